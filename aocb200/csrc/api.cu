@@ -1,0 +1,35 @@
+// Error reporting, version and device check of libaocb200.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace aoc {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace aoc
+
+extern "C" int aoc_version(void) { return 100; }
+
+extern "C" const char* aoc_last_error_string(void) { return aoc::g_err; }
+
+extern "C" int aoc_check_device(int dev) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        aoc::set_error("aoc_check_device: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return AOC_ELAUNCH;
+    }
+    if (prop.major != 10) {
+        aoc::set_error("aoc_check_device: device %d is sm_%d%d, this library is built for sm_100a only", dev,
+                       prop.major, prop.minor);
+        return AOC_EARCH;
+    }
+    return AOC_OK;
+}

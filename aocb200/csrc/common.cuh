@@ -1,0 +1,58 @@
+// Shared device/host helpers for libaocb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/aocb200.h"
+
+#define AOC_WRONG_LABEL_PAD 5.0e4f  // reference: networks/layers/matching.py:25
+
+namespace aoc {
+
+void set_error(const char* fmt, ...);
+
+inline int launch_status(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return AOC_ELAUNCH;
+    }
+    return AOC_OK;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 2*sigmoid(x)-1 exactly as the reference composes it: (sigmoid(x) - 0.5) * 2   (matching.py:2508)
+__device__ __forceinline__ float sig2(float x) {
+    float s = 1.0f / (1.0f + expf(-x));
+    return (s - 0.5f) * 2.0f;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+}  // namespace aoc
+
+#define AOC_CHECK_ARG(cond, msg)                         \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            aoc::set_error("%s: %s", __func__, msg);     \
+            return AOC_EINVAL;                           \
+        }                                                \
+    } while (0)

@@ -1,0 +1,236 @@
+// Per-(sample, channel) statistics over NHWC maps and the per-(sample, channel) affine kernels built on them:
+// GroupNorm, GCT gate, IA gate / conditioning-block scale (x * a[n,c]), global average pool, masked GAP.
+// All are HBM-bound reduction / streaming kernels: 128-bit coalesced loads, fixed reduction order
+// (deterministic), no tensor cores.
+//
+// Replaces: nn.GroupNorm call sites (networks/layers/gct.py:68-91, aocnet.py:19-25, decoding_module.py),
+// GCT (networks/layers/gct.py:17-36), IA_gate (networks/layers/attention.py:12-17), the FiLM scale of
+// conditioning_block (networks/aoc/conditioning_layer.py:63-86) and the masked global average pool of
+// conditioning_layer (networks/aoc/conditioning_layer.py:24-48).
+#include "common.cuh"
+
+namespace aoc {
+
+// part layout: [N][S][2][C] doubles (sum, sum of squares).  MASKED: weight = phi[n,p] > thr[n] (strict).
+template <bool MASKED>
+__global__ void __launch_bounds__(256) channel_stats_partial(const float* __restrict__ x, int HW, int C, int ldx,
+                                                              int PB, const float* __restrict__ phi,
+                                                              const float* __restrict__ thr,
+                                                              double* __restrict__ part) {
+    extern __shared__ float sm[];  // [PL][2][C]
+    const int n = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    const int Q = C >> 2;
+    const int PL = 256 / Q;
+    const int tid = threadIdx.x;
+    const int q = tid % Q, pl = tid / Q;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
+    if (pl < PL) {
+        int pend = min((s + 1) * PB, HW);
+        float th = MASKED ? __ldg(thr + n) : 0.f;
+        for (int p = s * PB + pl; p < pend; p += PL) {
+            if (MASKED) {
+                if (!(__ldg(phi + (size_t)n * HW + p) > th)) continue;
+            }
+            float4 v = ldg4(x + ((size_t)n * HW + p) * ldx + q * 4);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y);
+            sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+        }
+        float* d = sm + (size_t)pl * 2 * C;
+        *reinterpret_cast<float4*>(d + q * 4) = sum;
+        *reinterpret_cast<float4*>(d + C + q * 4) = sq;
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * C; c += 256) {
+        double a = 0.0;
+        for (int l = 0; l < PL; ++l) a += (double)sm[(size_t)l * 2 * C + c];
+        part[((size_t)(n * S + s)) * 2 * C + c] = a;
+    }
+}
+
+// stats: [N][2][C] doubles
+__global__ void channel_stats_final(const double* __restrict__ part, int S, int C2, double* __restrict__ stats) {
+    int n = blockIdx.y;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C2) return;
+    double a = 0.0;
+    for (int s = 0; s < S; ++s) a += part[((size_t)(n * S + s)) * C2 + c];
+    stats[(size_t)n * C2 + c] = a;
+}
+
+// GroupNorm coefficients: y = x*a + b with a = rstd*gamma, b = beta - mean*a   (biased variance, eps inside sqrt)
+__global__ void gn_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int C, int groups, int HW, float eps,
+                                 float* __restrict__ a, float* __restrict__ b) {
+    int n = blockIdx.x;
+    int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            s += stats[(size_t)n * 2 * C + c];
+            q += stats[(size_t)n * 2 * C + C + c];
+        }
+        double cnt = (double)cpg * HW;
+        double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float fmean = (float)mean;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            float ga = gamma[c] * rstd;
+            a[(size_t)n * C + c] = ga;
+            b[(size_t)n * C + c] = beta[c] - fmean * ga;
+        }
+    }
+}
+
+// GCT gate (gct.py:17-36, mode l2): embedding = sqrt(sum x^2 + eps)*alpha; norm = gamma/sqrt(mean_c(emb^2)+eps);
+// gate = 1 + tanh(emb*norm + beta).  `pre` (optional, [N,C]) is a per-channel scale already applied to x
+// analytically (x_eff = pre*x): sumsq_eff = pre^2*sumsq, and the returned gate is multiplied by pre.
+__global__ void gct_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ pre, int C, float eps, float* __restrict__ a) {
+    __shared__ double red[32];
+    __shared__ double s_mean;
+    int n = blockIdx.x;
+    double loc = 0.0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sq = stats[(size_t)n * 2 * C + C + c];
+        if (pre) { double pz = (double)pre[(size_t)n * C + c]; sq *= pz * pz; }
+        float e = sqrtf((float)sq + eps) * alpha[c];
+        loc += (double)e * (double)e;
+    }
+    loc = warp_sum_d(loc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) t += red[i];
+        s_mean = t / C;
+    }
+    __syncthreads();
+    float inv = 1.0f / sqrtf((float)s_mean + eps);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sq = stats[(size_t)n * 2 * C + C + c];
+        float pz = 1.f;
+        if (pre) { pz = pre[(size_t)n * C + c]; sq *= (double)pz * (double)pz; }
+        float e = sqrtf((float)sq + eps) * alpha[c];
+        float nrm = gamma[c] * inv;
+        a[(size_t)n * C + c] = pz * (1.0f + tanhf(e * nrm + beta[c]));
+    }
+}
+
+__global__ void gap_from_stats_kernel(const double* __restrict__ stats, int C, float inv_hw, float* __restrict__ out) {
+    int n = blockIdx.y;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) out[(size_t)n * C + c] = (float)(stats[(size_t)n * 2 * C + c] * (double)inv_hw);
+}
+
+// y[n,p,c] = x[n,p,c]*a[n,c] + b[n,c] (+ res[n,p,c]*ra[n,c]) (ReLU)
+__global__ void affine_nc_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                                 const float* __restrict__ res, const float* __restrict__ res_scale,
+                                 float* __restrict__ y, int HW, int C, int ldx, int ldy, int ldres, int relu,
+                                 long long total4) {
+    int C4 = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        long long pix = i / C4;
+        int n = (int)(pix / HW);
+        float4 v = ldg4(x + (size_t)pix * ldx + c);
+        float4 av = ldg4(a + (size_t)n * C + c);
+        float4 o;
+        if (b) {
+            float4 bv = ldg4(b + (size_t)n * C + c);
+            o.x = fmaf(v.x, av.x, bv.x); o.y = fmaf(v.y, av.y, bv.y);
+            o.z = fmaf(v.z, av.z, bv.z); o.w = fmaf(v.w, av.w, bv.w);
+        } else {
+            o.x = v.x * av.x; o.y = v.y * av.y; o.z = v.z * av.z; o.w = v.w * av.w;
+        }
+        if (res) {
+            float4 r = ldg4(res + (size_t)pix * ldres + c);
+            if (res_scale) {
+                float4 rs = ldg4(res_scale + (size_t)n * C + c);
+                r.x *= rs.x; r.y *= rs.y; r.z *= rs.z; r.w *= rs.w;
+            }
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(y + (size_t)pix * ldy + c) = o;
+    }
+}
+
+static int stats_slab(int HW) {
+    int pb = 256;
+    while ((long long)cdiv(HW, pb) > 1024) pb *= 2;
+    return pb;
+}
+
+}  // namespace aoc
+
+using namespace aoc;
+
+extern "C" size_t aoc_channel_stats_workspace_bytes(int N, int HW, int C) {
+    int PB = stats_slab(HW);
+    size_t S = (size_t)cdiv(HW, PB);
+    return (size_t)N * S * 2 * C * sizeof(double);
+}
+
+// stats out: [N][2][C] doubles (sum, sumsq).  phi/thr optional (masked sum: only pixels with phi > thr[n]).
+extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int ldx, const float* phi,
+                                     const float* thr, double* stats, void* workspace, size_t ws_bytes,
+                                     cudaStream_t stream) {
+    AOC_CHECK_ARG(x && stats && workspace, "null pointer");
+    AOC_CHECK_ARG(C % 4 == 0 && C >= 4 && C <= 1024 && ldx % 4 == 0, "C must be a multiple of 4 in [4,1024]");
+    AOC_CHECK_ARG((((uintptr_t)x) & 15) == 0, "x must be 16-byte aligned");
+    AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
+    AOC_CHECK_ARG((phi == nullptr) == (thr == nullptr), "phi and thr go together");
+    int PB = stats_slab(HW);
+    int S = cdiv(HW, PB);
+    int PL = 256 / (C / 4);
+    size_t smem = (size_t)PL * 2 * C * sizeof(float);
+    dim3 grid(S, N);
+    double* part = (double*)workspace;
+    if (phi)
+        channel_stats_partial<true><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, phi, thr, part);
+    else
+        channel_stats_partial<false><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, nullptr, nullptr, part);
+    dim3 g2(cdiv(2 * C, 256), N);
+    channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
+    return launch_status("aoc_channel_stats_f32");
+}
+
+extern "C" int aoc_gn_coeffs_f32(const double* stats, const float* gamma, const float* beta, int N, int C, int groups,
+                                 int HW, float eps, float* a, float* b, cudaStream_t stream) {
+    AOC_CHECK_ARG(stats && gamma && beta && a && b, "null pointer");
+    AOC_CHECK_ARG(groups > 0 && C % groups == 0, "C must be divisible by groups");
+    gn_coeffs_kernel<<<N, 64, 0, stream>>>(stats, gamma, beta, C, groups, HW, eps, a, b);
+    return launch_status("aoc_gn_coeffs_f32");
+}
+
+extern "C" int aoc_gct_coeffs_f32(const double* stats, const float* alpha, const float* gamma, const float* beta,
+                                  const float* pre_scale, int N, int C, float eps, float* a, cudaStream_t stream) {
+    AOC_CHECK_ARG(stats && alpha && gamma && beta && a, "null pointer");
+    gct_coeffs_kernel<<<N, 256, 0, stream>>>(stats, alpha, gamma, beta, pre_scale, C, eps, a);
+    return launch_status("aoc_gct_coeffs_f32");
+}
+
+extern "C" int aoc_gap_from_stats_f32(const double* stats, int N, int C, int HW, float* out, cudaStream_t stream) {
+    AOC_CHECK_ARG(stats && out, "null pointer");
+    dim3 g(cdiv(C, 256), N);
+    gap_from_stats_kernel<<<g, 256, 0, stream>>>(stats, C, 1.0f / (float)HW, out);
+    return launch_status("aoc_gap_from_stats_f32");
+}
+
+extern "C" int aoc_affine_nc_f32(const float* x, const float* a, const float* b, const float* residual,
+                                 const float* res_scale, float* y, int N, int HW, int C, int ldx, int ldy, int ldres,
+                                 int relu, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && a && y, "null pointer");
+    AOC_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && (!residual || ldres % 4 == 0), "C/ld must be multiples of 4");
+    AOC_CHECK_ARG(((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0, "pointers must be 16-byte aligned");
+    long long total4 = (long long)N * HW * (C / 4);
+    int blocks = (int)((total4 + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    affine_nc_kernel<<<blocks, 256, 0, stream>>>(x, a, b, residual, res_scale, y, HW, C, ldx, ldy, ldres, relu, total4);
+    return launch_status("aoc_affine_nc_f32");
+}

@@ -1,0 +1,240 @@
+// Layout conversion and resampling kernels (NHWC fp32).
+// Replaces F.interpolate call sites: bilinear align_corners=True (deeplab/aspp.py:72, deeplab/decoder.py:35,
+// layers/aspp.py:66, matching.py:2729-2732,2849, aocnet.py:103), bicubic align_corners=True
+// (decoding_module.py:163), nearest for label maps (aocnet.py:128-135, matching.py:2805).
+#include "common.cuh"
+
+namespace aoc {
+
+// image [3,H,W] (NCHW, N=1) -> [H*W,4] with a zero 4th channel (so the stem conv takes the float4 path)
+__global__ void nchw3_to_nhwc4_kernel(const float* __restrict__ x, float* __restrict__ y, int HW) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    float4 v = make_float4(__ldg(x + p), __ldg(x + HW + p), __ldg(x + 2 * (size_t)HW + p), 0.f);
+    *reinterpret_cast<float4*>(y + (size_t)p * 4) = v;
+}
+
+// generic [N,C,HW] -> [N,HW,C] (smem-tiled transpose)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int ldy) {
+    __shared__ float t[32][33];
+    int n = blockIdx.z;
+    int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) t[i][threadIdx.x] = x[((size_t)n * C + c) * HW + p];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)n * HW + p) * ldy + c] = t[threadIdx.x][i];
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int ldx) {
+    __shared__ float t[32][33];
+    int n = blockIdx.z;
+    int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int p = p0 + i, c = c0 + threadIdx.x;
+        if (c < C && p < HW) t[i][threadIdx.x] = x[((size_t)n * HW + p) * ldx + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, p = p0 + threadIdx.x;
+        if (c < C && p < HW) y[((size_t)n * C + c) * HW + p] = t[threadIdx.x][i];
+    }
+}
+
+__device__ __forceinline__ void lin_coords(int dst, float scale, int in, int& i0, int& i1, float& l0, float& l1) {
+    float real = scale * (float)dst;          // align_corners=True: src = dst*(in-1)/(out-1)
+    i0 = min((int)real, in - 1);
+    i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+    l1 = fminf(fmaxf(real - (float)i0, 0.f), 1.f);
+    l0 = 1.f - l1;
+}
+
+// Bilinear, align_corners=True.  If ids != nullptr the source is a lookup: src[n,pix,:] = table[ids[n,pix]] (zero
+// row when ids >= n_table) -- used for `seq_prev_frame_embedding_inst` (aocnet.py:325) without materialising it.
+__global__ void resize_bilinear_kernel(const float* __restrict__ x, const uint8_t* __restrict__ ids,
+                                       const float* __restrict__ table, int n_table, float* __restrict__ y, int N,
+                                       int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy, float sh, float sw) {
+    int C4 = C >> 2;
+    long long total = (long long)N * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        long long pix = i / C4;
+        int xo = (int)(pix % Wo);
+        int yo = (int)((pix / Wo) % Ho);
+        int n = (int)(pix / ((long long)Wo * Ho));
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        lin_coords(yo, sh, Hi, y0, y1, ly0, ly1);
+        lin_coords(xo, sw, Wi, x0, x1, lx0, lx1);
+        float4 v00, v01, v10, v11;
+        size_t b = (size_t)n * Hi * Wi;
+        if (ids) {
+            auto fetch = [&](int yy, int xx) {
+                int id = ids[b + (size_t)yy * Wi + xx];
+                return id < n_table ? ldg4(table + (size_t)id * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            v00 = fetch(y0, x0); v01 = fetch(y0, x1); v10 = fetch(y1, x0); v11 = fetch(y1, x1);
+        } else {
+            v00 = ldg4(x + (b + (size_t)y0 * Wi + x0) * ldx + c);
+            v01 = ldg4(x + (b + (size_t)y0 * Wi + x1) * ldx + c);
+            v10 = ldg4(x + (b + (size_t)y1 * Wi + x0) * ldx + c);
+            v11 = ldg4(x + (b + (size_t)y1 * Wi + x1) * ldx + c);
+        }
+        float4 o;
+        o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+        o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+        o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+        o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+        *reinterpret_cast<float4*>(y + (size_t)pix * ldy + c) = o;
+    }
+}
+
+__device__ __forceinline__ void cubic_coeffs(float t, float w[4]) {
+    const float A = -0.75f;
+    float x = t + 1.f;
+    w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+    x = t;
+    w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 1.f - t;
+    w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 2.f - t;
+    w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+// Bicubic (A=-0.75), align_corners=True, border indices clamped.
+__global__ void resize_bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi, int Ho,
+                                      int Wo, int C, int ldx, int ldy, float sh, float sw) {
+    int C4 = C >> 2;
+    long long total = (long long)N * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        long long pix = i / C4;
+        int xo = (int)(pix % Wo);
+        int yo = (int)((pix / Wo) % Ho);
+        int n = (int)(pix / ((long long)Wo * Ho));
+        float ry = sh * (float)yo, rx = sw * (float)xo;
+        int iy = (int)floorf(ry), ix = (int)floorf(rx);
+        float wy[4], wx[4];
+        cubic_coeffs(ry - (float)iy, wy);
+        cubic_coeffs(rx - (float)ix, wx);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        size_t b = (size_t)n * Hi * Wi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int yy = min(max(iy - 1 + j, 0), Hi - 1);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int xx = min(max(ix - 1 + k, 0), Wi - 1);
+                float4 v = ldg4(x + (b + (size_t)yy * Wi + xx) * ldx + c);
+                r.x = fmaf(wx[k], v.x, r.x); r.y = fmaf(wx[k], v.y, r.y);
+                r.z = fmaf(wx[k], v.z, r.z); r.w = fmaf(wx[k], v.w, r.w);
+            }
+            o.x = fmaf(wy[j], r.x, o.x); o.y = fmaf(wy[j], r.y, o.y);
+            o.z = fmaf(wy[j], r.z, o.z); o.w = fmaf(wy[j], r.w, o.w);
+        }
+        *reinterpret_cast<float4*>(y + (size_t)pix * ldy + c) = o;
+    }
+}
+
+// Nearest resize of a uint8 label map, PyTorch 'nearest' rule: src = min(floor(dst * (in/out)), in-1) in float.
+__global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int Hi, int Wi,
+                                         int Ho, int Wo, float sh, float sw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ho * Wo) return;
+    int yo = i / Wo, xo = i - yo * Wo;
+    int yi = (Ho == Hi) ? yo : min((int)floorf((float)yo * sh), Hi - 1);
+    int xi = (Wo == Wi) ? xo : min((int)floorf((float)xo * sw), Wi - 1);
+    y[i] = x[(size_t)yi * Wi + xi];
+}
+
+static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
+
+}  // namespace aoc
+
+using namespace aoc;
+
+extern "C" int aoc_image_to_nhwc4_f32(const float* x, float* y, int H, int W, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && H > 0 && W > 0, "bad args");
+    nchw3_to_nhwc4_kernel<<<cdiv((long long)H * W, 256), 256, 0, stream>>>(x, y, H * W);
+    return launch_status("aoc_image_to_nhwc4_f32");
+}
+
+extern "C" int aoc_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int HW, int ldy, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && N > 0 && C > 0 && HW > 0, "bad args");
+    dim3 g(cdiv(HW, 32), cdiv(C, 32), N), b(32, 8);
+    nchw_to_nhwc_kernel<<<g, b, 0, stream>>>(x, y, C, HW, ldy);
+    return launch_status("aoc_nchw_to_nhwc_f32");
+}
+
+extern "C" int aoc_nhwc_to_nchw_f32(const float* x, float* y, int N, int C, int HW, int ldx, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && N > 0 && C > 0 && HW > 0, "bad args");
+    dim3 g(cdiv(HW, 32), cdiv(C, 32), N), b(32, 8);
+    nhwc_to_nchw_kernel<<<g, b, 0, stream>>>(x, y, C, HW, ldx);
+    return launch_status("aoc_nhwc_to_nchw_f32");
+}
+
+extern "C" int aoc_resize_bilinear_nhwc_f32(const float* x, const uint8_t* ids, const float* table, int n_table,
+                                            float* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy,
+                                            cudaStream_t stream) {
+    AOC_CHECK_ARG((x || (ids && table)) && y, "null pointer");
+    AOC_CHECK_ARG(C % 4 == 0 && ldy % 4 == 0 && (ids || ldx % 4 == 0), "C/ld must be multiples of 4");
+    long long total = (long long)N * Ho * Wo * (C / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    resize_bilinear_kernel<<<blocks, 256, 0, stream>>>(x, ids, table, n_table, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy,
+                                                       ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+    return launch_status("aoc_resize_bilinear_nhwc_f32");
+}
+
+extern "C" int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                                           int ldx, int ldy, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y, "null pointer");
+    AOC_CHECK_ARG(C % 4 == 0 && ldy % 4 == 0 && ldx % 4 == 0, "C/ld must be multiples of 4");
+    long long total = (long long)N * Ho * Wo * (C / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    resize_bicubic_kernel<<<blocks, 256, 0, stream>>>(x, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, ac_scale(Hi, Ho),
+                                                      ac_scale(Wi, Wo));
+    return launch_status("aoc_resize_bicubic_nhwc_f32");
+}
+
+extern "C" int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo,
+                                     cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad args");
+    resize_nearest_u8_kernel<<<cdiv((long long)Ho * Wo, 256), 256, 0, stream>>>(x, y, Hi, Wi, Ho, Wo,
+                                                                             (float)Hi / (float)Ho,
+                                                                             (float)Wi / (float)Wo);
+    return launch_status("aoc_resize_nearest_u8");
+}
+
+namespace aoc {
+__global__ void copy_channels_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int C, int ldx,
+                                     int ldy) {
+    int C4 = C >> 2;
+    long long total = rows * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C4) * 4;
+        long long r = i / C4;
+        *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = ldg4(x + (size_t)r * ldx + c);
+    }
+}
+}  // namespace aoc
+
+// y[r, 0:C] = x[r, 0:C] with independent row strides (channel-slice copy into / out of concat buffers)
+extern "C" int aoc_copy_channels_f32(const float* x, float* y, long long rows, int C, int ldx, int ldy,
+                                     cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && rows > 0 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "bad args");
+    long long total = rows * (C / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    aoc::copy_channels_kernel<<<blocks, 256, 0, stream>>>(x, y, rows, C, ldx, ldy);
+    return aoc::launch_status("aoc_copy_channels_f32");
+}

@@ -1,0 +1,177 @@
+/* libaocb200 -- C ABI of the B200-native (sm_100a) AOC-Net per-frame inference kernels.
+ *
+ * The reference (JerryX1110/Robust-Video-Object-Segmentation) is pure Python/PyTorch and has no FFI of its own:
+ * its boundary for this path is the Python duck type `AOCNet.forward_for_eval` (networks/aoc/aocnet.py:84) and the
+ * op callables imported at networks/aoc/aocnet.py:6-8.  Each entry point below replaces one of those torch call
+ * sites (cited per function; paths relative to AOC-Net/complete_project/AOCNet/).  The Python host
+ * (aocb200/model.py) binds them with ctypes; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (except where "host" is stated); no hidden allocation;
+ *   - activations are fp32 NHWC ("pixel-major": [N][H*W][C]) with an explicit row stride `ld*` in floats, so a
+ *     kernel can read/write a channel slice of a wider concat buffer; label maps are uint8 object ids
+ *     (0 = background slot, 1..K objects, anything >= O, e.g. 125 = "uncertain", belongs to no object);
+ *   - O = K + 1 object slots, O <= AOC_MAX_OBJECTS; the embedding width is fixed at 100
+ *     (cfg.MODEL_SEMANTIC_EMBEDDING_DIM);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous and re-entrant per
+ *     stream; workspaces are sized by the matching *_workspace_bytes();
+ *   - return value: AOC_OK or a negative AOC_E* code; aoc_last_error_string() describes the last failure of the
+ *     calling thread.  Nothing throws or aborts.  There is no CPU fallback: without a CUDA device every launch
+ *     returns AOC_ELAUNCH.
+ */
+#ifndef AOCB200_H_
+#define AOCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define AOC_OK 0
+#define AOC_EINVAL (-1)   /* bad argument (shape, alignment, null pointer, workspace too small) */
+#define AOC_ELAUNCH (-2)  /* CUDA launch/runtime failure (cudaGetLastError) */
+#define AOC_EARCH (-3)    /* device is not sm_100 */
+
+#define AOC_MAX_OBJECTS 16   /* O = K+1 slots */
+#define AOC_KMEANS_MAX_K 16  /* cluster_num, matching.py:507 */
+#define AOC_PROXY_SLOTS 36   /* per object: 16 centroids, 16 centroid_avg, 1 mean proxy, 3 pad */
+#define AOC_META_INTS (2 * AOC_MAX_OBJECTS + 3)
+
+int aoc_version(void);
+const char* aoc_last_error_string(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
+int aoc_check_device(int dev);
+
+/* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv.cu) */
+/* nn.Conv2d (+ folded FrozenBatchNorm2d bias, + residual, + ReLU): resnet.py:23-42,108-123; deeplab/aspp.py:62-74;
+ * deeplab/decoder.py:32-41; layers/gct.py:68-91; layers/aspp.py:57-70; decoding_module.py:162-190,228-240.
+ * x [N][H][W][ldx>=Cin], w [Cout][kh][kw][Cin], y [N][Ho][Wo][ldy>=Cout]; in_scale (optional) [N][Cin] multiplies the
+ * input per (sample, channel) -- a fused IA/GCT gate.  fp32 FMA, exact-path. */
+int aoc_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, const float* residual,
+                        const float* in_scale, float* y, int N, int H, int W, int Cin, int ldx, int Cout, int ldy,
+                        int ldres, int kh, int kw, int stride, int pad, int dil, int relu, cudaStream_t stream);
+/* Same contract on the tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM).  w_packed comes from
+ * aoc_conv_pack_weights_tf32x3 (size aoc_conv_packed_weight_bytes).  Requires Cin % 4 == 0. */
+size_t aoc_conv_packed_weight_bytes(int Cout, int K);
+int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int K, void* w_packed, cudaStream_t stream);
+int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
+                       const float* in_scale, float* y, int N, int H, int W, int Cin, int ldx, int Cout, int ldy,
+                       int ldres, int kh, int kw, int stride, int pad, int dil, int relu, cudaStream_t stream);
+/* depthwise 3x3 pad 1 + bias (aocnet.py:19 seperate_conv); w [C][3][3] */
+int aoc_dwconv3x3_nhwc_f32(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C,
+                           cudaStream_t stream);
+/* F.max_pool2d(x, 3, 2, 1) (resnet.py:113) */
+int aoc_maxpool3x3s2_nhwc_f32(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- statistics / affine (norm.cu) */
+size_t aoc_channel_stats_workspace_bytes(int N, int HW, int C);
+/* stats [N][2][C] doubles = per-(sample, channel) sum and sum of squares over HW; with (phi, thr) only pixels with
+ * phi[n,p] > thr[n] are summed (masked GAP of conditioning_layer.py:38-43). */
+int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int ldx, const float* phi, const float* thr,
+                          double* stats, void* workspace, size_t ws_bytes, cudaStream_t stream);
+/* nn.GroupNorm as y = x*a[n,c] + b[n,c] */
+int aoc_gn_coeffs_f32(const double* stats, const float* gamma, const float* beta, int N, int C, int groups, int HW,
+                      float eps, float* a, float* b, cudaStream_t stream);
+/* GCT gate (layers/gct.py:17-36): a[n,c] = pre*(1 + tanh(emb*norm + beta)) */
+int aoc_gct_coeffs_f32(const double* stats, const float* alpha, const float* gamma, const float* beta,
+                       const float* pre_scale, int N, int C, float eps, float* a, cudaStream_t stream);
+/* adaptive_avg_pool2d(x, 1) from the statistics */
+int aoc_gap_from_stats_f32(const double* stats, int N, int C, int HW, float* out, cudaStream_t stream);
+/* y = x*a[n,c] (+ b[n,c]) (+ residual*res_scale[n,c]) (ReLU) */
+int aoc_affine_nc_f32(const float* x, const float* a, const float* b, const float* residual, const float* res_scale,
+                      float* y, int N, int HW, int C, int ldx, int ldy, int ldres, int relu, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- FiLM conditioning (film.cu) */
+/* phi_layer: 1x1 conv C->1 (conditioning_layer.py:27) */
+int aoc_cond_phi_f32(const float* x, const float* w, const float* b, float* phi, int N, int HW, int C, int ldx,
+                     cudaStream_t stream);
+/* torch.topk(vals, k)[..., -1] per row (conditioning_layer.py:32-36); k is 1-based */
+int aoc_kth_largest_f32(const float* vals, int N, int L, int k, float* out, cudaStream_t stream);
+/* nn.Linear; act 0 = identity, 1 = 1 + tanh (IA_gate attention.py:12-17, conditioning_block :82-85) */
+int aoc_linear_f32(const float* x, const float* W, const float* b, float* y, int N, int M, int K, int ldx, int ldy,
+                   int act, cudaStream_t stream);
+/* out[n] = sum_n' v[n'] - v[n] (conditioning_layer.py:69, decoding_module.py IA9/IA10/IA11 heads) */
+int aoc_delta_sum_f32(const float* v, float* out, int N, int C, int ldo, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- layout / resampling (resize.cu) */
+int aoc_image_to_nhwc4_f32(const float* x_chw3, float* y_hwc4, int H, int W, cudaStream_t stream);
+int aoc_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int HW, int ldy, cudaStream_t stream);
+int aoc_nhwc_to_nchw_f32(const float* x, float* y, int N, int C, int HW, int ldx, cudaStream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=True); with (ids, table) the source is table[ids[pixel]] */
+int aoc_resize_bilinear_nhwc_f32(const float* x, const uint8_t* ids, const float* table, int n_table, float* y, int N,
+                                 int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy, cudaStream_t stream);
+/* F.interpolate(mode='bicubic', align_corners=True) (decoding_module.py:163) */
+int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi, int Ho, int Wo, int C, int ldx,
+                                int ldy, cudaStream_t stream);
+/* torch.cat along channels: copy a channel slice between buffers with different row strides */
+int aoc_copy_channels_f32(const float* x, float* y, long long rows, int C, int ldx, int ldy, cudaStream_t stream);
+/* F.interpolate(mode='nearest') on label maps (aocnet.py:128-135) */
+int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- reference bank (matching.cu) */
+size_t aoc_bank_workspace_bytes(int total_pixels, int O);
+/* Object-sorted index of all bank pixels (matching.py:2486-2495, :533-545).  ids: uint8 [total_pixels] (frames
+ * concatenated).  meta_out (device int32[AOC_META_INTS]): [o] = rows of object o, [AOC_MAX_OBJECTS+o] = first sorted
+ * row of object o (segments padded to `align` rows), [2*MAX+1] = padded row count, [2*MAX+2] = valid pixels. */
+int aoc_bank_index_build(const uint8_t* ids, int total_pixels, int O, int align, int* meta_out, int* row_src,
+                         int cap_rows, int* nat2sorted, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int aoc_bank_gather_f32(const float* emb_all, const int* row_src, int rows, float* S, float* r2, cudaStream_t stream);
+/* tcgen05 operand image of the same rows (3xTF32 hi/lo split, K-chunked core-matrix layout) */
+size_t aoc_bank_tc_bytes(int rows);
+int aoc_bank_gather_tc(const float* emb_all, const int* row_src, int rows, void* S_tc, float* r2, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- matching (matching.cu, umma_match.cu) */
+/* global_matching_for_eval (matching.py:2384-2510): out [HW][O] */
+int aoc_global_match_simt_f32(const float* q, int HW, const float* S, const float* r2, const int* meta,
+                              const float* bias, int O, float* mins_ws, float* out, cudaStream_t stream);
+int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev,
+                        const int* meta_host, const float* bias, int O, void* q_tc_ws, float* mins_ws, float* out,
+                        cudaStream_t stream);
+size_t aoc_global_match_tc_workspace_bytes(int HW);
+int aoc_global_match_finalize_f32(const float* mins, const int* meta, const float* bias, int HW, int O, float* out,
+                                  cudaStream_t stream);
+/* cluster level (matching.py:602-637) and k=1 proxy level (matching.py:149-197): out_cluster [HW][O][2], out_proxy [HW][O] */
+int aoc_proxy_match_f32(const float* q, int HW, const float* P, const int* pvalid, const float* bias, int O,
+                        float* out_cluster, float* out_proxy, cudaStream_t stream);
+size_t aoc_head_pool_workspace_bytes(int total_pixels);
+/* calculate_attention_head_for_eval_p_m (attention.py:155-189): masked means written into head rows */
+int aoc_head_pool_f32(const float* emb, const uint8_t* ids, int total_pixels, int O, float eps, float* head,
+                      int ld_head, int off_pos, int off_neg, float* pos_out, int ld_pos, void* workspace,
+                      size_t ws_bytes, cudaStream_t stream);
+int aoc_row_sqnorm_f32(const float* x, int rows, float* out, cudaStream_t stream);
+/* local_matching / local_matching_proxy on the half-resolution grid (matching.py:2710-2851): out [hh*ww][ld_out], o*6+ch */
+int aoc_local_match_f32(const float* xq, const float* yp, const float* x2, const float* y2, const uint8_t* ids, int hh,
+                        int ww, int O, const float* bias, float* out, int ld_out, cudaStream_t stream);
+/* foreground2background + concat (matching.py:9-23, aocnet.py:349-358): out [O][HW][24] */
+int aoc_prehead_assemble_f32(const float* g, const float* gc, const float* gp, const float* loc, const float* locp,
+                             int ld_loc, const uint8_t* prev_ids, int HW, int O, float* out, cudaStream_t stream);
+int aoc_broadcast_rows_f32(const float* x, float* y, int N, int HW, int C, int ldx, int ldy, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- adaptive object proxies (kmeans.cu) */
+size_t aoc_kmeans_workspace_bytes(int max_rows_per_object, int O);
+/* scipy.cluster.vq.kmeans2(X_i, k, 'points', iter) per object + centroid_avg (matching.py:533-595) */
+int aoc_kmeans_proxies_f32(const float* S, const int* meta, const int* nat2sorted, const int* kk, const int* init_idx,
+                           int O, int max_rows_per_object, int iters, float* cent, int* labels, float* P, int* pvalid,
+                           void* workspace, size_t ws_bytes, cudaStream_t stream);
+
+/* ---------------------------------------------------------------- output head (head.cu) */
+int aoc_dyn_logits_f32(const float* x, const float* wfg, const float* wbg, float* fg, float* bg, float* logits, int O,
+                       int HW, int C, int ldx, cudaStream_t stream);
+int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8_t* label, int O, int h, int w, int H, int W,
+                             cudaStream_t stream);
+
+/* ---------------------------------------------------------------- tcgen05 self-test (umma_gemm.cu) */
+/* C[M][N] = A[M][K] * B[N][K]^T with the 3xTF32 tcgen05 pipeline (M%128==0, N%128==0, K%8==0); test hook. */
+int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, int M, int N, int K, int variant,
+                         cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOCB200_H_ */
