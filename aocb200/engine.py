@@ -1,0 +1,601 @@
+"""Host side of the B200 engine: weight repacking and the per-frame kernel schedule.
+
+Everything numerical runs in libaocb200.so (hand-written sm_100a CUDA, C ABI in include/aocb200.h); torch is used
+for device memory, the current stream and a few index/dtype conversions on label maps.  The schedule mirrors
+AOCNet.forward_for_eval / before_seghead_process (networks/aoc/aocnet.py:84-372) and CalibrationDecoding.forward
+(networks/aoc/decoding_module.py:96-225) of the reference, with SURVEY.md Appendix A's repair set.
+"""
+import numpy as np
+import torch
+
+from .lib import lib
+from .params import EMB, HEAD
+
+MAXO = 16
+PROXY_SLOTS = 36
+META_INTS = 2 * MAXO + 3
+BANK_ALIGN = 256
+
+
+class T:
+    """NHWC fp32 activation: a channel slice [off, off+C) of rows of width ld inside `buf`."""
+    __slots__ = ("buf", "N", "H", "W", "C", "ld", "off")
+
+    def __init__(self, buf, N, H, W, C, ld=None, off=0):
+        self.buf, self.N, self.H, self.W, self.C = buf, N, H, W, C
+        self.ld = C if ld is None else ld
+        self.off = off
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.off
+
+    @property
+    def HW(self):
+        return self.H * self.W
+
+    def slice(self, off, C):
+        return T(self.buf, self.N, self.H, self.W, C, self.ld, self.off + off)
+
+    def nchw(self):
+        """torch view [N,C,H,W] (channels-last strides) of a full-width activation."""
+        assert self.off == 0 and self.ld == self.C
+        return self.buf.view(self.N, self.H, self.W, self.C).permute(0, 3, 1, 2)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class Weights:
+    """Device-resident, repacked parameters (done once per state_dict)."""
+
+    def __init__(self, sd, device):
+        f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+        self.dev = device
+        self.conv = {}      # name -> (w [Cout,kh,kw,Cin], bias|None, (Cout,kh,kw,Cin))
+        self.vec = {}       # misc vectors / matrices
+        has = lambda k: k in sd
+
+        def add_conv(name, bn=None, pad_cin=None):
+            w = f(name + ".weight")
+            b = f(name + ".bias") if has(name + ".bias") else None
+            if bn is not None:  # FrozenBatchNorm2d (normalization.py:17-23) folded into the conv
+                scale = f(bn + ".weight") * (f(bn + ".running_var") + 1e-5).rsqrt()
+                shift = f(bn + ".bias") - f(bn + ".running_mean") * scale
+                w = w * scale.view(-1, 1, 1, 1)
+                b = shift if b is None else b * scale + shift
+            if pad_cin is not None and w.shape[1] < pad_cin:
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_cin - w.shape[1], w.shape[2], w.shape[3])], 1)
+            w = w.permute(0, 2, 3, 1).contiguous()
+            self.conv[name] = (w, None if b is None else b.contiguous(), tuple(w.shape))
+
+        bb = "feature_extracter.backbone"
+        add_conv(bb + ".conv1", bb + ".bn1", pad_cin=4)
+        for lname, blocks in (("layer1", 3), ("layer2", 4), ("layer3", 23), ("layer4", 3)):
+            for i in range(blocks):
+                p = "%s.%s.%d" % (bb, lname, i)
+                for j in (1, 2, 3):
+                    add_conv("%s.conv%d" % (p, j), "%s.bn%d" % (p, j))
+                if has(p + ".downsample.0.weight"):
+                    add_conv(p + ".downsample.0", p + ".downsample.1")
+        a = "feature_extracter.aspp"
+        for i in (1, 2, 3, 4):
+            add_conv("%s.aspp%d.atrous_conv" % (a, i), "%s.aspp%d.bn" % (a, i))
+        add_conv(a + ".global_avg_pool.1", a + ".global_avg_pool.2")
+        add_conv(a + ".conv1", a + ".bn1")
+        d = "feature_extracter.decoder"
+        add_conv(d + ".conv1", d + ".bn1")
+        add_conv(d + ".last_conv.0", d + ".last_conv.1")
+        add_conv(d + ".last_conv.4", d + ".last_conv.5")
+        add_conv("embedding_conv")
+        add_conv("dynamic_prehead.conv")
+        self.vec["seperate_conv.weight"] = f("seperate_conv.weight").reshape(256, 9).contiguous()
+        self.vec["seperate_conv.bias"] = f("seperate_conv.bias").contiguous()
+        h = "dynamic_seghead"
+        for k in sd.keys():
+            if not k.startswith(h + "."):
+                continue
+            if k.endswith(".weight") and sd[k].dim() == 4 and "phi_layer" not in k:
+                add_conv(k[:-len(".weight")])
+        # everything else as flat fp32 tensors
+        for k in sd.keys():
+            if k.startswith("feature_extracter."):
+                continue
+            base = k.rsplit(".", 1)[0]
+            if base in self.conv:
+                continue
+            self.vec[k] = f(k).reshape(-1).contiguous() if sd[k].dim() != 2 else f(k).contiguous()
+        self.vec["dis_bias"] = torch.cat([f("bg_bias").reshape(1), f("fg_bias").reshape(1).expand(MAXO - 1)]).contiguous()
+        # conditioning_block: CL_2 / CL_3 are input independent under repair R7 (they return mlp_layer.bias), so
+        # mlp_layer([c1, c2, c3]) = W[:, :C] c1 + (W[:, C:] [c2; c3] + b)      (conditioning_layer.py:63-86)
+        for blk, C in (("CLB2", 256), ("CLB3", 256), ("CLB4", 512), ("CLB5", 512)):
+            p = "%s.%s" % (h, blk)
+            Wm, bm = f(p + ".mlp_layer.weight"), f(p + ".mlp_layer.bias")
+            c23 = torch.cat([f(p + ".CL_2.mlp_layer.bias"), f(p + ".CL_3.mlp_layer.bias")])
+            self.vec[p + ".fold.weight"] = Wm[:, :C].contiguous()
+            self.vec[p + ".fold.bias"] = (bm + Wm[:, C:] @ c23).contiguous()
+
+
+class Bank:
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.refs, self.masks = [], []
+        self.emb_all = self.ids_all = None
+        self.hw = None
+        self.n = 0
+
+
+class Engine:
+    def __init__(self, state_dict, device):
+        self.dev = torch.device(device)
+        self.L = lib()
+        self.L.check_device(self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        self.w = Weights(state_dict, self.dev)
+        self.bank = Bank()
+        self.kmeans_iters = 20
+        self.cluster_num = 16
+        self.debug = {}
+        self.keep_debug = False
+        self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
+        self._ws = {}
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def empty(self, n, dtype=torch.float32):
+        return torch.empty(int(n), dtype=dtype, device=self.dev)
+
+    def new(self, N, H, W, C):
+        return T(self.empty(N * H * W * C), N, H, W, C)
+
+    def ws(self, name, nbytes):
+        """persistent scratch (never handed to the caller)"""
+        b = self._ws.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+            self._ws[name] = b
+        return b
+
+    # ------------------------------------------------------------------ layer helpers
+    def conv(self, x, name, stride=1, pad=0, dil=1, relu=False, res=None, in_scale=None, out=None):
+        w, b, (Cout, kh, kw, Cin) = self.w.conv[name]
+        assert Cin == x.C, (name, Cin, x.C)
+        Ho = (x.H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (x.W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        if out is None:
+            out = self.new(x.N, Ho, Wo, Cout)
+        assert out.C == Cout and out.H == Ho and out.W == Wo and out.N == x.N
+        self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
+                               x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw, stride,
+                               pad, dil, 1 if relu else 0, self.stream)
+        return out
+
+    def stats(self, x, phi=None, thr=None):
+        L = self.L
+        n = L.channel_stats_workspace_bytes(x.N, x.HW, x.C)
+        ws = self.ws("stats", n)
+        st = self.empty(x.N * 2 * x.C, torch.float64)
+        L.channel_stats_f32(x.ptr, x.N, x.HW, x.C, x.ld, _p(phi), _p(thr), st.data_ptr(), ws.data_ptr(), n, self.stream)
+        return st
+
+    def affine(self, x, a, b=None, res=None, res_scale=None, relu=False, out=None):
+        if out is None:
+            out = self.new(x.N, x.H, x.W, x.C)
+        self.L.affine_nc_f32(x.ptr, a.data_ptr(), _p(b), None if res is None else res.ptr, _p(res_scale), out.ptr,
+                             x.N, x.HW, x.C, x.ld, out.ld, 0 if res is None else res.ld, 1 if relu else 0, self.stream)
+        return out
+
+    def gn(self, x, name, groups, relu=False, res=None, out=None):
+        st = self.stats(x)
+        a, b = self.empty(x.N * x.C), self.empty(x.N * x.C)
+        self.L.gn_coeffs_f32(st.data_ptr(), self.w.vec[name + ".weight"].data_ptr(),
+                             self.w.vec[name + ".bias"].data_ptr(), x.N, x.C, groups, x.HW, 1e-5, a.data_ptr(),
+                             b.data_ptr(), self.stream)
+        return self.affine(x, a, b, res=res, relu=relu, out=out)
+
+    def gct_gate(self, x, name, st=None, pre=None):
+        st = self.stats(x) if st is None else st
+        a = self.empty(x.N * x.C)
+        v = self.w.vec
+        self.L.gct_coeffs_f32(st.data_ptr(), v[name + ".alpha"].data_ptr(), v[name + ".gamma"].data_ptr(),
+                              v[name + ".beta"].data_ptr(), _p(pre), x.N, x.C, 1e-5, a.data_ptr(), self.stream)
+        return a
+
+    def gap(self, x, st=None):
+        st = self.stats(x) if st is None else st
+        out = self.empty(x.N * x.C)
+        self.L.gap_from_stats_f32(st.data_ptr(), x.N, x.C, x.HW, out.data_ptr(), self.stream)
+        return out
+
+    def linear(self, x, wname, N, act=0, ldx=None, weight=None, bias=None, out=None, ldy=None):
+        W = self.w.vec[wname + ".weight"] if weight is None else weight
+        b = self.w.vec[wname + ".bias"] if bias is None else bias
+        M, K = W.shape
+        if out is None:
+            out = self.empty(N * M)
+        self.L.linear_f32(x.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(), N, M, K, K if ldx is None else ldx,
+                          M if ldy is None else ldy, act, self.stream)
+        return out
+
+    def resize_bilinear(self, x, Ho, Wo, out=None):
+        if out is None:
+            out = self.new(x.N, Ho, Wo, x.C)
+        self.L.resize_bilinear_nhwc_f32(x.ptr, None, None, 0, out.ptr, x.N, x.H, x.W, Ho, Wo, x.C, x.ld, out.ld,
+                                        self.stream)
+        return out
+
+    def copy_channels(self, x, out):
+        self.L.copy_channels_f32(x.ptr, out.ptr, x.N * x.HW, x.C, x.ld, out.ld, self.stream)
+        return out
+
+    # ------------------------------------------------------------------ backbone (networks/deeplab/*)
+    def _res_block(self, x, p, stride, dil):
+        y = self.conv(x, p + ".conv1", relu=True)
+        y = self.conv(y, p + ".conv2", stride=stride, pad=dil, dil=dil, relu=True)
+        if (p + ".downsample.0") in self.w.conv:
+            x = self.conv(x, p + ".downsample.0", stride=stride)
+        return self.conv(y, p + ".conv3", relu=True, res=x)
+
+    def extract_feature(self, img):
+        """aocnet.py:109-112 + deeplab.py:27-38.  img [1,3,H,W] fp32 -> (emb T[1,h,w,100], low T[1,h,w,256])"""
+        L = self.L
+        assert img.dim() == 4 and img.shape[0] == 1 and img.shape[1] == 3
+        img = img.to(device=self.dev, dtype=torch.float32).contiguous()
+        H, W = int(img.shape[2]), int(img.shape[3])
+        x4 = self.new(1, H, W, 4)
+        L.image_to_nhwc4_f32(img.data_ptr(), x4.ptr, H, W, self.stream)
+        bb = "feature_extracter.backbone"
+        x = self.conv(x4, bb + ".conv1", stride=2, pad=3, relu=True)
+        Hp, Wp = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
+        xp = self.new(1, Hp, Wp, 64)
+        L.maxpool3x3s2_nhwc_f32(x.ptr, xp.ptr, 1, x.H, x.W, 64, self.stream)
+        x = xp
+        low = None
+        for lname, blocks, stride, dils in (("layer1", 3, 1, [1, 1, 1]), ("layer2", 4, 2, [1] * 4),
+                                            ("layer3", 23, 2, [1] * 23), ("layer4", 3, 1, [2, 4, 8])):
+            for b in range(blocks):
+                x = self._res_block(x, "%s.%s.%d" % (bb, lname, b), stride if b == 0 else 1, dils[b])
+            if lname == "layer1":
+                low = x
+        # ASPP (deeplab/aspp.py:62-74): 4 atrous branches + image pooling, written into one concat buffer
+        a = "feature_extracter.aspp"
+        cat = self.new(1, x.H, x.W, 1280)
+        self.conv(x, a + ".aspp1.atrous_conv", relu=True, out=cat.slice(0, 256))
+        for i, dl in ((2, 6), (3, 12), (4, 18)):
+            self.conv(x, "%s.aspp%d.atrous_conv" % (a, i), pad=dl, dil=dl, relu=True, out=cat.slice(256 * (i - 1), 256))
+        g = T(self.gap(x), 1, 1, 1, 2048)
+        g = self.conv(g, a + ".global_avg_pool.1", relu=True)
+        self.resize_bilinear(g, x.H, x.W, out=cat.slice(1024, 256))
+        y = self.conv(cat, a + ".conv1", relu=True)
+        # decoder (deeplab/decoder.py:32-41)
+        d = "feature_extracter.decoder"
+        cat2 = self.new(1, low.H, low.W, 304)
+        self.resize_bilinear(y, low.H, low.W, out=cat2.slice(0, 256))
+        self.conv(low, d + ".conv1", relu=True, out=cat2.slice(256, 48))
+        y = self.conv(cat2, d + ".last_conv.0", pad=1, relu=True)
+        y = self.conv(y, d + ".last_conv.4", pad=1, relu=True)
+        # semantic embedding (aocnet.py:19-25)
+        v = self.w.vec
+        z = self.new(1, y.H, y.W, 256)
+        L.dwconv3x3_nhwc_f32(y.ptr, v["seperate_conv.weight"].data_ptr(), v["seperate_conv.bias"].data_ptr(), z.ptr, 1,
+                             y.H, y.W, 256, self.stream)
+        z = self.gn(z, "bn1", 32, relu=True)
+        z = self.conv(z, "embedding_conv")
+        emb = self.gn(z, "bn2", 25, relu=True)
+        return emb, low
+
+    # ------------------------------------------------------------------ matching (aocnet.py:128-358)
+    def _as_nhwc_emb(self, e, h, w):
+        """[1,100,h,w] tensor (ours: channels-last view; foreign: NCHW) -> flat NHWC tensor [h*w*100]"""
+        assert e.shape[0] == 1 and e.shape[1] == EMB and e.shape[2] == h and e.shape[3] == w, tuple(e.shape)
+        if e.device == self.dev and e.dtype == torch.float32 and e.stride()[1] == 1 and e.stride()[3] == EMB and \
+                e.stride()[2] == w * EMB:
+            return e.permute(0, 2, 3, 1).reshape(-1)
+        src = e.to(device=self.dev, dtype=torch.float32).contiguous()
+        out = self.empty(h * w * EMB)
+        self.L.nchw_to_nhwc_f32(src.data_ptr(), out.data_ptr(), 1, EMB, h * w, EMB, self.stream)
+        return out
+
+    def _label_ids(self, mask, h, w, out=None):
+        """[1,1,H,W] integer label map -> uint8 ids [h*w] (nearest resize, aocnet.py:128-135)"""
+        m = mask.to(device=self.dev)
+        if m.dtype != torch.uint8:
+            m = m.clamp(0, 255).to(torch.uint8)
+        m = m.contiguous()
+        Hm, Wm = int(m.shape[-2]), int(m.shape[-1])
+        if out is None:
+            out = self.empty(h * w, torch.uint8)
+        self.L.resize_nearest_u8(m.data_ptr(), out.data_ptr(), Hm, Wm, h, w, self.stream)
+        return out
+
+    def _sync_bank(self, ref_embeddings, ref_masks, h, w):
+        bk = self.bank
+        hw = h * w
+        ok = bk.hw == hw and len(ref_embeddings) >= bk.n and len(ref_embeddings) == len(ref_masks)
+        if ok:
+            for i in range(bk.n):
+                if bk.refs[i] is not ref_embeddings[i] or bk.masks[i] is not ref_masks[i]:
+                    ok = False
+                    break
+        if not ok:
+            bk.reset()
+            bk.hw = hw
+        F = len(ref_embeddings)
+        cap = 0 if bk.emb_all is None else bk.ids_all.numel() // hw
+        if F > cap:
+            ncap = max(F, 2 * cap, 8)
+            emb_all = self.empty(ncap * hw * EMB)
+            ids_all = self.empty(ncap * hw, torch.uint8)
+            if bk.n:
+                emb_all[:bk.n * hw * EMB].copy_(bk.emb_all[:bk.n * hw * EMB])
+                ids_all[:bk.n * hw].copy_(bk.ids_all[:bk.n * hw])
+            bk.emb_all, bk.ids_all = emb_all, ids_all
+        for i in range(bk.n, F):
+            e = self._as_nhwc_emb(ref_embeddings[i], h, w)
+            self.L.copy_channels_f32(e.data_ptr(), bk.emb_all.data_ptr() + 4 * i * hw * EMB, hw, EMB, EMB, EMB,
+                                     self.stream)
+            self._label_ids(ref_masks[i], h, w, out=bk.ids_all[i * hw:(i + 1) * hw])
+            bk.refs.append(ref_embeddings[i])
+            bk.masks.append(ref_masks[i])
+        bk.n = F
+        return F
+
+    def match_features(self, ref_embeddings, ref_masks, prev_embedding, prev_mask, emb, K):
+        """-> (x T[O,h,w,164] decoder input, head [O*400], prev_ids) ; aocnet.py:128-362"""
+        L, st = self.L, self.stream
+        O = K + 1
+        assert 1 <= O <= MAXO, "at most %d objects" % (MAXO - 1)
+        h, w, hw = emb.H, emb.W, emb.HW
+        q = emb
+        bias = self.w.vec["dis_bias"]
+        F = self._sync_bank(ref_embeddings, ref_masks, h, w)
+        bk = self.bank
+        total = F * hw
+        # --- object-sorted bank
+        meta = self.empty(META_INTS, torch.int32)
+        cap_rows = total + O * BANK_ALIGN
+        row_src = self.empty(cap_rows, torch.int32)
+        nat2sorted = self.empty(total, torch.int32)
+        nws = L.bank_workspace_bytes(total, O)
+        L.bank_index_build(bk.ids_all.data_ptr(), total, O, BANK_ALIGN, meta.data_ptr(), row_src.data_ptr(), cap_rows,
+                           nat2sorted.data_ptr(), self.ws("bank", nws).data_ptr(), nws, st)
+        self._meta_host.copy_(meta, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()   # the host needs the per-object counts (RNG draws)
+        mh = self._meta_host.numpy()
+        counts = [int(mh[o]) for o in range(O)]
+        rows = int(mh[2 * MAXO + 1])
+        S = self.empty(max(rows, 1) * EMB)
+        r2 = self.empty(max(rows, 1))
+        L.bank_gather_f32(bk.emb_all.data_ptr(), row_src.data_ptr(), rows, S.data_ptr(), r2.data_ptr(), st)
+        # --- pixel-level global matching (matching.py:2384)
+        g = self.empty(hw * O)
+        mins = self.empty(hw * O)
+        L.global_match_simt_f32(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), bias.data_ptr(), O,
+                                mins.data_ptr(), g.data_ptr(), st)
+        # --- adaptive object proxies (matching.py:533-595): k chain + init rows from numpy's global RNG
+        kk = np.zeros(MAXO, dtype=np.int32)
+        init = np.zeros((MAXO, 16), dtype=np.int32)
+        k = self.cluster_num
+        for o in range(O):
+            k = min(k, counts[o])                     # matching.py:556 -- carries over to later objects
+            if k == 0:
+                continue
+            kk[o] = k
+            init[o, :k] = np.random.choice(counts[o], size=int(k), replace=False)   # == scipy _kpoints
+        kk_d = torch.from_numpy(kk).to(self.dev, non_blocking=True)
+        init_d = torch.from_numpy(init).to(self.dev, non_blocking=True)
+        cent = self.empty(MAXO * 16 * EMB)
+        labels = self.empty(max(rows, 1), torch.int32)
+        P = torch.zeros(MAXO * PROXY_SLOTS * EMB, dtype=torch.float32, device=self.dev)
+        pvalid = torch.zeros(MAXO * PROXY_SLOTS, dtype=torch.int32, device=self.dev)
+        maxrows = max(counts) if counts else 0
+        kws = L.kmeans_workspace_bytes(maxrows, O)
+        L.kmeans_proxies_f32(S.data_ptr(), meta.data_ptr(), nat2sorted.data_ptr(), kk_d.data_ptr(), init_d.data_ptr(),
+                             O, maxrows, self.kmeans_iters, cent.data_ptr(), labels.data_ptr(), P.data_ptr(),
+                             pvalid.data_ptr(), self.ws("kmeans", kws).data_ptr(), kws, st)
+        # --- attention heads / k=1 proxies (attention.py:155-189)
+        head = self.empty(O * HEAD)
+        prev_e = self._as_nhwc_emb(prev_embedding, h, w)
+        prev_ids = self._label_ids(prev_mask, h, w)
+        hws = L.head_pool_workspace_bytes(max(total, hw))
+        hbuf = self.ws("headpool", hws)
+        L.head_pool_f32(bk.emb_all.data_ptr(), bk.ids_all.data_ptr(), total, O, 1e-5, head.data_ptr(), HEAD, 0, EMB,
+                        P.data_ptr() + 4 * 32 * EMB, PROXY_SLOTS * EMB, hbuf.data_ptr(), hws, st)
+        prev_pos = self.empty(O * EMB)
+        L.head_pool_f32(prev_e.data_ptr(), prev_ids.data_ptr(), hw, O, 1e-5, head.data_ptr(), HEAD, 2 * EMB, 3 * EMB,
+                        prev_pos.data_ptr(), EMB, hbuf.data_ptr(), hws, st)
+        # --- cluster-level + proxy-level matching (matching.py:602-637, :149-197)
+        gc = self.empty(hw * O * 2)
+        gp = self.empty(hw * O)
+        L.proxy_match_f32(q.ptr, hw, P.data_ptr(), pvalid.data_ptr(), bias.data_ptr(), O, gc.data_ptr(), gp.data_ptr(), st)
+        # --- local matching on the half-resolution grid (matching.py:2710-2851)
+        hh, ww = h // 2 + 1, w // 2 + 1
+        ldl = (6 * O + 3) // 4 * 4
+        xq = self.resize_bilinear(q, hh, ww)
+        yp = self.resize_bilinear(T(prev_e, 1, h, w, EMB), hh, ww)
+        ids_lr = self.empty(hh * ww, torch.uint8)
+        L.resize_nearest_u8(prev_ids.data_ptr(), ids_lr.data_ptr(), h, w, hh, ww, st)
+        x2, y2 = self.empty(hh * ww), self.empty(hh * ww)
+        L.row_sqnorm_f32(xq.ptr, hh * ww, x2.data_ptr(), st)
+        L.row_sqnorm_f32(yp.ptr, hh * ww, y2.data_ptr(), st)
+        loc_lr = T(torch.zeros(hh * ww * ldl, dtype=torch.float32, device=self.dev), 1, hh, ww, ldl)
+        L.local_match_f32(xq.ptr, yp.ptr, x2.data_ptr(), y2.data_ptr(), ids_lr.data_ptr(), hh, ww, O, bias.data_ptr(),
+                          loc_lr.ptr, ldl, st)
+        loc = self.resize_bilinear(loc_lr, h, w)
+        # local proxy matching: previous-frame pixels replaced by their object's mean proxy (aocnet.py:325-337)
+        yq = self.new(1, hh, ww, EMB)
+        L.resize_bilinear_nhwc_f32(None, prev_ids.data_ptr(), prev_pos.data_ptr(), O, yq.ptr, 1, h, w, hh, ww, EMB, EMB,
+                                   EMB, st)
+        L.row_sqnorm_f32(yq.ptr, hh * ww, y2.data_ptr(), st)
+        locp_lr = T(torch.zeros(hh * ww * ldl, dtype=torch.float32, device=self.dev), 1, hh, ww, ldl)
+        L.local_match_f32(xq.ptr, yq.ptr, x2.data_ptr(), y2.data_ptr(), ids_lr.data_ptr(), hh, ww, O, bias.data_ptr(),
+                          locp_lr.ptr, ldl, st)
+        locp = self.resize_bilinear(locp_lr, h, w)
+        # --- fg->bg, concat, pre-head (aocnet.py:349-362, decoding_module.py:228-240)
+        pre = self.new(O, h, w, 24)
+        L.prehead_assemble_f32(g.data_ptr(), gc.data_ptr(), gp.data_ptr(), loc.ptr, locp.ptr, ldl, prev_ids.data_ptr(),
+                               hw, O, pre.ptr, st)
+        x = self.new(O, h, w, EMB + 64)
+        t = self.conv(pre, "dynamic_prehead.conv")
+        self.gn(t, "dynamic_prehead.bn", 16, relu=True, out=x.slice(EMB, 64))
+        L.broadcast_rows_f32(q.ptr, x.ptr, O, hw, EMB, q.ld, x.ld, st)
+        if self.keep_debug:
+            self.debug.update(g=g, gc=gc, gp=gp, loc=loc, locp=locp, pre=pre, head=head, P=P, pvalid=pvalid,
+                              labels=labels, cent=cent, meta=mh.copy(), S=S, r2=r2, nat2sorted=nat2sorted, kk=kk,
+                              init=init, prev_ids=prev_ids, ldl=ldl)
+        return x, head, prev_ids
+
+    # ------------------------------------------------------------------ calibration decoder (decoding_module.py)
+    def ia_gate(self, x, head_t, ldh, name):
+        a = self.linear(head_t, name + ".IA", x.N, act=1, ldx=ldh)
+        return self.affine(x, a)
+
+    def gn_bottleneck(self, x, p, stride=1, dil=1):
+        """layers/gct.py:68-91"""
+        gate = self.gct_gate(x, p + ".GCT1")
+        y = self.conv(x, p + ".conv1", in_scale=gate)
+        y = self.gn(y, p + ".bn1", 32, relu=True)
+        y = self.conv(y, p + ".conv2", stride=stride, pad=dil, dil=dil)
+        y = self.gn(y, p + ".bn2", 32, relu=True)
+        y = self.conv(y, p + ".conv3")
+        if (p + ".downsample.0") in self.w.conv:
+            r = self.conv(x, p + ".downsample.0", stride=stride)
+            r = self.gn(r, p + ".downsample.1", 32)
+        else:
+            r = x
+        return self.gn(y, p + ".bn3", 32, relu=True, res=r)
+
+    def cond_block(self, x, p, beta=0.3):
+        """conditioning_block / conditioning_layer (conditioning_layer.py:24-86) with CL_2/CL_3 folded"""
+        L, v = self.L, self.w.vec
+        O, hw, C = x.N, x.HW, x.C
+        phi = self.empty(O * hw)
+        L.cond_phi_f32(x.ptr, v[p + ".CL_1.phi_layer.weight"].data_ptr(), v[p + ".CL_1.phi_layer.bias"].data_ptr(),
+                       phi.data_ptr(), O, hw, C, x.ld, self.stream)
+        thr = self.empty(O)
+        rank = max(1, int(beta * x.W * x.H))
+        L.kth_largest_f32(phi.data_ptr(), O, hw, rank, thr.data_ptr(), self.stream)
+        st = self.stats(x, phi, thr)
+        gapm = self.gap(x, st)                                   # masked sum / (h*w)
+        c1 = self.linear(gapm, p + ".CL_1.mlp_layer", O)
+        a = self.linear(c1, p + ".fold", O, act=1)
+        return self.affine(x, a)
+
+    def delta_head(self, x, head):
+        """cat([head, sum_objects(GAP(x)) - GAP(x)]) -> [O, 400 + C]"""
+        O, C = x.N, x.C
+        px = self.gap(x)
+        out = self.empty(O * (HEAD + C))
+        self.L.copy_channels_f32(head.data_ptr(), out.data_ptr(), O, HEAD, HEAD, HEAD + C, self.stream)
+        self.L.delta_sum_f32(px.data_ptr(), out.data_ptr() + 4 * HEAD, O, C, HEAD + C, self.stream)
+        return out
+
+    def decoder_aspp(self, x, p):
+        """layers/aspp.py:57-70"""
+        O = x.N
+        st = self.stats(x)
+        cat = self.new(O, x.H, x.W, 640)
+        for i, d in ((1, 0), (2, 6), (3, 12), (4, 18)):
+            q = "%s.aspp%d" % (p, i)
+            gate = self.gct_gate(x, q + ".GCT", st=st)
+            y = self.conv(x, q + ".atrous_conv", pad=d, dil=max(d, 1), in_scale=gate)
+            self.gn(y, q + ".bn", 32, relu=True, out=cat.slice(128 * (i - 1), 128))
+        g = T(self.gap(x, st), O, 1, 1, x.C)
+        g = self.conv(g, p + ".global_avg_pool.1", relu=True)
+        self.resize_bilinear(g, x.H, x.W, out=cat.slice(512, 128))
+        gate = self.gct_gate(cat, p + ".GCT")
+        y = self.conv(cat, p + ".conv1", in_scale=gate)
+        return self.gn(y, p + ".bn1", 32, relu=True)
+
+    def modulator(self, x, mem, head, p, tag):
+        """decoding_module.py:192-210"""
+        cat = self.new(x.N, x.H, x.W, x.C + mem.C)
+        self.copy_channels(x, cat.slice(0, x.C))
+        self.copy_channels(mem, cat.slice(x.C, mem.C))
+        x = cat
+        for i in (1, 2, 3):
+            x = self.ia_gate(x, head, HEAD, "%s.%s_Reweight_Layer_%d" % (p, tag, i))
+            x = self.gn_bottleneck(x, "%s.%s_Bottleneck_%d" % (p, tag, i))
+        return x
+
+    def _mem_T(self, m, like):
+        """caller-held memory tensor ([O,256,h2,w2] view of ours, or foreign NCHW) -> T or None"""
+        if m is None or tuple(m.shape) != (like.N, like.C, like.H, like.W):
+            return None
+        if m.device == self.dev and m.dtype == torch.float32 and m.stride()[1] == 1 and m.stride()[3] == like.C:
+            return T(m.permute(0, 2, 3, 1).reshape(-1), like.N, like.H, like.W, like.C)
+        src = m.to(device=self.dev, dtype=torch.float32).contiguous()
+        out = self.new(like.N, like.H, like.W, like.C)
+        self.L.nchw_to_nhwc_f32(src.data_ptr(), out.ptr, like.N, like.C, like.HW, like.C, self.stream)
+        return out
+
+    def calibration_decoding(self, x, head, memory, low):
+        """decoding_module.py:96-149 -> (logits tensor [O*h*w] as [O][h][w], [mem0, mem1] as T)"""
+        L, v = self.L, self.w.vec
+        p = "dynamic_seghead"
+        O, h, w = x.N, x.H, x.W
+        x = self.ia_gate(x, head, HEAD, p + ".IA1")
+        x = self.gn_bottleneck(x, p + ".layer1")
+        x = self.cond_block(x, p + ".CLB2")
+        x = self.gn_bottleneck(x, p + ".layer2", 1, 2)
+        x = self.cond_block(x, p + ".CLB3")
+        x = self.gn_bottleneck(x, p + ".layer3", 2, 1)
+        x = self.cond_block(x, p + ".CLB4")
+        x = self.gn_bottleneck(x, p + ".layer4", 1, 2)
+        x = self.cond_block(x, p + ".CLB5")
+        x = self.gn_bottleneck(x, p + ".layer5", 1, 4)
+        dh = self.delta_head(x, head)
+        x = self.ia_gate(x, dh, HEAD + x.C, p + ".IA9")
+        x = self.decoder_aspp(x, p + ".ASPP")
+        cur1 = x
+        m0 = self._mem_T(memory[0], cur1) or cur1
+        x = self.modulator(x, m0, head, p, "M1")
+        cur2 = x
+        m1 = self._mem_T(memory[1], cur2) or cur2
+        x = self.modulator(x, m1, head, p, "M2")
+        # decoder_final (decoding_module.py:162-190, repair R9)
+        cat = self.new(O, h, w, 512)                       # [low (256, broadcast over objects) | x upsampled (256)]
+        L.broadcast_rows_f32(low.ptr, cat.ptr, O, h * w, 256, low.ld, 512, self.stream)
+        xu = cat.slice(256, 256)
+        L.resize_bicubic_nhwc_f32(x.ptr, xu.ptr, O, x.H, x.W, h, w, 256, x.ld, 512, self.stream)
+        gate = self.gct_gate(cat, p + ".GCT_sc")
+        sc = self.conv(cat, p + ".conv_sc", in_scale=gate)
+        cat2 = self.new(O, h, w, 320)                      # [x (256) | sc (64)]
+        self.copy_channels(xu, cat2.slice(0, 256))
+        self.gn(sc, p + ".bn_sc", 16, relu=True, out=cat2.slice(256, 64))
+        x = cat2
+        x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA10")
+        x = self.gn(self.conv(x, p + ".conv1", pad=1), p + ".bn1", 32, relu=True)
+        x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA11")
+        x = self.gn(self.conv(x, p + ".conv2", pad=1), p + ".bn2", 32, relu=True)
+        wfg = self.linear(head, p + ".IA_final_fg", O)
+        wbg = self.linear(head, p + ".IA_final_bg", O)
+        fg, bg, logits = self.empty(O * h * w), self.empty(O * h * w), self.empty(O * h * w)
+        L.dyn_logits_f32(x.ptr, wfg.data_ptr(), wbg.data_ptr(), fg.data_ptr(), bg.data_ptr(), logits.data_ptr(), O,
+                         h * w, x.C, x.ld, self.stream)
+        return logits, [cur1, m1]
+
+    # ------------------------------------------------------------------ per-frame entry (aocnet.py:84-107)
+    def forward_for_eval(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
+                         pred_size, gt_ids):
+        emb, low = self.extract_feature(current_frame)
+        emb_out = emb.nchw()
+        if prev_embedding is None:
+            return None, emb_out, memory_prev_list
+        K = int(gt_ids[0]) if not isinstance(gt_ids, int) else gt_ids
+        O = K + 1
+        x, head, _ = self.match_features(ref_embeddings, ref_masks, prev_embedding, prev_mask, emb, K)
+        logits, mem = self.calibration_decoding(x, head, list(memory_prev_list[0]), low)
+        H, W = int(pred_size[0]), int(pred_size[1])
+        probs = torch.empty((1, O, H, W), dtype=torch.float32, device=self.dev)
+        label = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
+        self.L.upsample_softmax_f32(logits.data_ptr(), probs.data_ptr(), label.data_ptr(), O, emb.H, emb.W, H, W,
+                                    self.stream)
+        self.last_logits = logits.view(1, O, emb.H, emb.W)
+        self.last_label = label
+        return probs, emb_out, [[mem[0].nchw(), mem[1].nchw()]]

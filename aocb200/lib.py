@@ -1,0 +1,82 @@
+"""ctypes binding of libaocb200.so -- the C ABI declared in include/aocb200.h.
+
+The prototypes are parsed from the header, so the header stays the single source of truth.  There is no
+fallback: if the shared library is missing or a call fails, this module raises.
+"""
+import ctypes
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(_HERE, "..", "include", "aocb200.h")
+LIB_PATH = os.path.join(_HERE, "libaocb200.so")
+
+_CT = {
+    "int": ctypes.c_int, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong,
+    "cudaStream_t": ctypes.c_void_p,
+}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [(argtype, argname), ...])} for every function declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"(?:^|;|\{)\s*((?:const\s+)?[A-Za-z_][\w ]*?[\s\*]+)(aoc_\w+)\s*\(([^)]*)\)\s*(?=;)", src, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        alist = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                mm = re.match(r"(.*?)(\w+)$", a)
+                alist.append((mm.group(1).strip(), mm.group(2)))
+        protos[name] = (ret, alist)
+    return protos
+
+
+def _ctype(t):
+    if "*" in t:
+        return ctypes.c_char_p if t.replace(" ", "") == "constchar*" else ctypes.c_void_p
+    t = t.replace("const ", "").strip()
+    return _CT[t]
+
+
+class AocError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise AocError("libaocb200.so is not built (run `python -m aocb200.build`); there is no fallback path")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        self.launches = 0
+        for name, (ret, args) in self.protos.items():
+            fn = getattr(self.cdll, name)
+            fn.restype = _ctype(ret) if ret != "int" else ctypes.c_int
+            fn.argtypes = [_ctype(t) for t, _ in args]
+            if ret == "int" and name not in ("aoc_version",):
+                setattr(self, name[4:], self._checked(fn, name))
+            else:
+                setattr(self, name[4:], fn)
+
+    def _checked(self, fn, name):
+        def call(*a):
+            rc = fn(*a)
+            if rc != 0:
+                raise AocError("%s failed (%d): %s" % (name, rc, self.cdll.aoc_last_error_string().decode()))
+            self.launches += 1
+            return rc
+        return call
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib

@@ -1,0 +1,61 @@
+"""The C-ABI library loads and exports every symbol include/aocb200.h declares; argument validation and the
+'no fallback' behaviour work without a GPU (no compute calls here)."""
+import ctypes
+import subprocess
+
+import pytest
+
+from aocb200.lib import LIB_PATH, AocError, parse_header
+
+
+def test_header_parses():
+    protos = parse_header()
+    assert len(protos) >= 45
+    for must in ("aoc_conv2d_nhwc_f32", "aoc_kmeans_proxies_f32", "aoc_global_match_simt_f32", "aoc_local_match_f32",
+                 "aoc_channel_stats_f32", "aoc_upsample_softmax_f32", "aoc_global_match_tc", "aoc_conv2d_nhwc_tc"):
+        assert must in protos, must
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    missing = [n for n in parse_header() if n not in exported]
+    assert not missing, missing
+    extra = [n for n in exported if n.startswith("aoc_") and n not in parse_header()]
+    assert not extra, "exported but not declared in include/aocb200.h: %s" % extra
+
+
+def test_version_and_error_string(built_lib):
+    assert built_lib.cdll.aoc_version() >= 100
+    with pytest.raises(AocError) as e:
+        built_lib.conv2d_nhwc_f32(None, None, None, None, None, None, 1, 8, 8, 4, 4, 4, 4, 0, 1, 1, 1, 0, 1, 0, None)
+    assert "null pointer" in str(e.value)
+    rc = built_lib.cdll.aoc_kth_largest_f32(ctypes.c_void_p(16), 1, 10, 11, ctypes.c_void_p(16), None)
+    assert rc == -1 and b"k must be" in built_lib.cdll.aoc_last_error_string()
+
+
+def test_workspace_queries(built_lib):
+    assert built_lib.channel_stats_workspace_bytes(6, 25773, 256) == 6 * 101 * 2 * 256 * 8
+    assert built_lib.bank_workspace_bytes(25773, 6) > 0
+    assert built_lib.kmeans_workspace_bytes(25773, 6) > 0
+    assert built_lib.head_pool_workspace_bytes(25773) > 0
+
+
+def test_no_cpu_fallback():
+    """Without CUDA the model must refuse to run rather than fall back."""
+    import torch
+    from aocb200.model import get_module
+    m = get_module()(None, None)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        m.forward_for_eval([[None, None]], [], [], None, None, torch.zeros(1, 3, 33, 33), [33, 33], torch.tensor([1]))
+
+
+def test_product_does_not_import_oracle():
+    import os
+    root = os.path.join(os.path.dirname(__file__), "..", "aocb200")
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), fn

@@ -1,0 +1,255 @@
+"""Per-kernel parity of the CUDA path (through the C ABI) against the CPU oracle / torch fp32 on the same seeded
+inputs.  Integer/index work is bit-exact; fp32 reductions are compared at 1e-4..1e-5 of the value range."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import from_T, report, to_T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(state_dict):
+    from aocb200.engine import Engine
+    return Engine(state_dict, torch.device("cuda:0"))
+
+
+def _conv_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu, res, scale, bias, ld_in=None, off_in=0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) if bias else None
+    sc = torch.rand(N, Cin, generator=g) + 0.5 if scale else None
+    xin = x * sc[:, :, None, None] if scale else x
+    want = F.conv2d(xin, w, b, stride, pad, dil)
+    r = torch.randn_like(want) if res else None
+    if res:
+        want = want + r
+    if relu:
+        want = F.relu(want)
+    name = "t.%d" % seed
+    eng.w.conv[name] = (w.permute(0, 2, 3, 1).contiguous().cuda(), None if b is None else b.cuda(), (Cout, k, k, Cin))
+    xt = to_T(x, eng, ld_in, off_in)
+    rt = to_T(r, eng) if res else None
+    out = to_T(torch.zeros_like(want), eng, ld=want.shape[1] + 8, off=4)
+    eng.conv(xt, name, stride=stride, pad=pad, dil=dil, relu=relu, res=rt,
+             in_scale=None if sc is None else sc.cuda().contiguous(), out=out)
+    torch.cuda.synchronize()
+    report("conv %dx%d s%d d%d %d->%d M=%d" % (k, k, stride, dil, Cin, Cout, N * want.shape[2] * want.shape[3]),
+           from_T(out), want, 2e-5 * max(1.0, want.abs().max().item()))
+
+
+def test_conv2d(eng):
+    _conv_case(eng, 1, 33, 41, 4, 64, 7, 2, 3, 1, True, False, False, True, seed=1)        # stem
+    _conv_case(eng, 1, 17, 23, 64, 256, 1, 1, 0, 1, True, True, False, True, seed=2)       # 1x1 + residual
+    _conv_case(eng, 1, 17, 23, 128, 128, 3, 2, 1, 1, True, False, False, True, seed=3)     # stride 2
+    _conv_case(eng, 1, 9, 13, 512, 512, 3, 1, 4, 4, True, False, False, True, seed=4)      # dilated
+    _conv_case(eng, 3, 19, 21, 164, 64, 1, 1, 0, 1, False, False, True, False, seed=5)     # in_scale, odd Cin
+    _conv_case(eng, 2, 19, 21, 256, 100, 1, 1, 0, 1, False, False, False, True, seed=6)    # Cout=100
+    _conv_case(eng, 2, 13, 17, 24, 64, 1, 1, 0, 1, False, False, False, True, seed=7)      # prehead
+    _conv_case(eng, 4, 31, 37, 320, 128, 3, 1, 1, 1, False, False, False, False, seed=8)   # big tile path
+    _conv_case(eng, 2, 1, 1, 512, 128, 1, 1, 0, 1, True, False, False, False, seed=9)      # 1x1 spatial
+    _conv_case(eng, 2, 12, 14, 48, 64, 3, 1, 6, 6, False, False, True, False, ld_in=80, off_in=16, seed=10)
+
+
+def test_dwconv_maxpool(eng):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 256, 15, 19, generator=g)
+    w = torch.randn(256, 1, 3, 3, generator=g)
+    b = torch.randn(256, generator=g)
+    want = F.conv2d(x, w, b, 1, 1, 1, 256)
+    xt = to_T(x, eng)
+    out = eng.new(1, 15, 19, 256)
+    eng.L.dwconv3x3_nhwc_f32(xt.ptr, w.reshape(256, 9).contiguous().cuda().data_ptr(), b.cuda().data_ptr(), out.ptr, 1,
+                             15, 19, 256, eng.stream)
+    report("dwconv3x3", from_T(out), want, 1e-5)
+    x = torch.randn(1, 64, 33, 41, generator=g)
+    want = F.max_pool2d(x, 3, 2, 1)
+    out = eng.new(1, want.shape[2], want.shape[3], 64)
+    eng.L.maxpool3x3s2_nhwc_f32(to_T(x, eng).ptr, out.ptr, 1, 33, 41, 64, eng.stream)
+    report("maxpool", from_T(out), want, 0.0)
+
+
+@pytest.mark.parametrize("N,C,groups,H,W", [(3, 256, 32, 31, 41), (1, 100, 25, 31, 41), (3, 64, 16, 17, 19),
+                                            (2, 64, 32, 9, 300), (2, 512, 32, 16, 27)])
+def test_groupnorm(eng, N, C, groups, H, W):
+    g = torch.Generator().manual_seed(C + N)
+    x = torch.randn(N, C, H, W, generator=g) * 3 + 1.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    r = torch.randn(N, C, H, W, generator=g)
+    want = F.relu(F.group_norm(x, groups, gamma, beta, 1e-5) + r)
+    eng.w.vec["t.gn.weight"], eng.w.vec["t.gn.bias"] = gamma.cuda(), beta.cuda()
+    out = eng.gn(to_T(x, eng, ld=C + 12, off=8), "t.gn", groups, relu=True, res=to_T(r, eng))
+    report("groupnorm C=%d g=%d" % (C, groups), from_T(out), want, 3e-5)
+
+
+def test_gct_and_gap(eng):
+    from oracle.aoc_oracle import _W, gct
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 640, 13, 17, generator=g)
+    sd = {"alpha": 1 + 0.1 * torch.randn(1, 640, 1, 1, generator=g), "gamma": 0.3 * torch.randn(1, 640, 1, 1, generator=g),
+          "beta": 0.3 * torch.randn(1, 640, 1, 1, generator=g)}
+    want = gct(x, _W(sd))
+    for k, v in sd.items():
+        eng.w.vec["t.gct." + k] = v.reshape(-1).cuda()
+    xt = to_T(x, eng)
+    gate = eng.gct_gate(xt, "t.gct")
+    report("gct", from_T(eng.affine(xt, gate)), want, 2e-5)
+    report("gap", eng.gap(xt).view(3, 640).cpu(), x.mean((2, 3)), 1e-6)
+    pre = torch.rand(3, 640, generator=g) + 0.5
+    want2 = gct(x * pre[:, :, None, None], _W(sd))
+    gate2 = eng.gct_gate(xt, "t.gct", pre=pre.cuda().contiguous())
+    report("gct(pre-scaled)", from_T(eng.affine(xt, gate2)), want2, 3e-5)
+
+
+@pytest.mark.parametrize("C,H,W", [(256, 31, 41), (512, 16, 21)])
+def test_conditioning_layer(eng, C, H, W):
+    from oracle.aoc_oracle import _W, conditioning_block
+    g = torch.Generator().manual_seed(C)
+    O = 4
+    x = torch.randn(O, C, H, W, generator=g)
+    head = torch.randn(O, 400, generator=g)
+    sd = {}
+    for nm, d in (("CL_1", C), ("CL_2", C), ("CL_3", 400)):
+        sd[nm + ".phi_layer.weight"] = torch.randn(1, d, 1, 1, generator=g) / d ** 0.5
+        sd[nm + ".phi_layer.bias"] = torch.randn(1, generator=g)
+        sd[nm + ".mlp_layer.weight"] = torch.randn(d, d, generator=g) / d ** 0.5
+        sd[nm + ".mlp_layer.bias"] = torch.randn(d, generator=g) * 0.1
+    sd["mlp_layer.weight"] = torch.randn(C, 2 * C + 400, generator=g) / (2 * C + 400) ** 0.5
+    sd["mlp_layer.bias"] = torch.randn(C, generator=g) * 0.1
+    want = conditioning_block(x, head, _W(sd))
+    p = "t.clb%d" % C
+    v = eng.w.vec
+    v[p + ".CL_1.phi_layer.weight"] = sd["CL_1.phi_layer.weight"].reshape(-1).cuda()
+    v[p + ".CL_1.phi_layer.bias"] = sd["CL_1.phi_layer.bias"].cuda()
+    v[p + ".CL_1.mlp_layer.weight"] = sd["CL_1.mlp_layer.weight"].cuda()
+    v[p + ".CL_1.mlp_layer.bias"] = sd["CL_1.mlp_layer.bias"].cuda()
+    Wm = sd["mlp_layer.weight"]
+    v[p + ".fold.weight"] = Wm[:, :C].contiguous().cuda()
+    v[p + ".fold.bias"] = (sd["mlp_layer.bias"] + Wm[:, C:] @ torch.cat([sd["CL_2.mlp_layer.bias"], sd["CL_3.mlp_layer.bias"]])).cuda()
+    out = eng.cond_block(to_T(x, eng), p)
+    report("conditioning_block C=%d" % C, from_T(out), want, 3e-5)
+
+
+def test_kth_largest_exact(eng):
+    g = torch.Generator().manual_seed(9)
+    vals = torch.randn(5, 6527, generator=g)
+    vals[1, :100] = vals[1, 100]          # ties
+    vals[2] = -vals[2].abs()
+    for k in (1, 2, 1958, 6527):
+        want = torch.topk(vals, k, dim=1)[0][:, -1]
+        out = eng.empty(5)
+        eng.L.kth_largest_f32(vals.cuda().data_ptr(), 5, 6527, k, out.data_ptr(), eng.stream)
+        assert torch.equal(out.cpu(), want), (k, out.cpu(), want)
+
+
+def test_resize(eng):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 100, 31, 41, generator=g)
+    for (Ho, Wo) in ((16, 21), (61, 81), (31, 41)):
+        want = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True)
+        report("bilinear->%dx%d" % (Ho, Wo), from_T(eng.resize_bilinear(to_T(x, eng), Ho, Wo)), want, 2e-6)
+    x1 = torch.randn(2, 128, 1, 1, generator=g)
+    report("bilinear 1x1->", from_T(eng.resize_bilinear(to_T(x1, eng), 7, 9)),
+           F.interpolate(x1, size=(7, 9), mode="bilinear", align_corners=True), 0.0)
+    x = torch.randn(2, 256, 16, 21, generator=g)
+    want = F.interpolate(x, size=(31, 41), mode="bicubic", align_corners=True)
+    out = eng.new(2, 31, 41, 256)
+    eng.L.resize_bicubic_nhwc_f32(to_T(x, eng).ptr, out.ptr, 2, 16, 21, 31, 41, 256, 256, 256, eng.stream)
+    report("bicubic", from_T(out), want, 5e-6)
+    lab = torch.randint(0, 200, (1, 1, 97, 129), generator=g, dtype=torch.uint8)
+    for (h, w) in ((25, 33), (13, 17), (97, 129)):
+        want = F.interpolate(lab.float(), size=(h, w), mode="nearest").to(torch.uint8).view(-1)
+        assert torch.equal(eng._label_ids(lab, h, w).cpu(), want), (h, w)
+
+
+def _rand_scene(seed, h, w, K, F_, absent=None, with125=True):
+    g = torch.Generator().manual_seed(seed)
+    embs = [F.relu(torch.randn(1, 100, h, w, generator=g)) for _ in range(F_ + 2)]
+    H, W = 4 * (h - 1) + 1, 4 * (w - 1) + 1
+    masks = []
+    for i in range(F_ + 1):
+        m = torch.randint(0, K + 1, (h // 4 + 1, w // 4 + 1), generator=g).float()
+        m = F.interpolate(m[None, None], size=(H, W), mode="nearest").long()
+        if absent is not None:
+            m[m == absent] = 0
+        if with125 and i > 0:
+            m[:, :, : H // 5, : W // 3] = 125
+        masks.append(m)
+    return embs, masks, (H, W)
+
+
+@pytest.mark.parametrize("seed,h,w,K,F_,absent", [(1, 25, 33, 3, 2, None), (2, 21, 29, 4, 1, 2), (3, 33, 37, 1, 3, None),
+                                                   (4, 17, 23, 5, 2, 5)])
+def test_match_features(eng, state_dict, seed, h, w, K, F_, absent):
+    """bank build, global / cluster / proxy / local matching, heads, fg2bg+concat -- vs the oracle's match_features"""
+    from aocb200.engine import T
+    from oracle.aoc_oracle import AOCOracle
+    embs, masks, _ = _rand_scene(seed, h, w, K, F_, absent)
+    ref_e, ref_m = embs[:F_], masks[:F_]
+    prev_e, prev_m, cur = embs[F_], masks[F_], embs[F_ + 1]
+    orc = AOCOracle(state_dict)
+    np.random.seed(seed)
+    pre_w, head_w, _ = orc.match_features(ref_e, ref_m, prev_e, prev_m, cur, K)
+    eng.bank.reset()
+    eng.keep_debug = True
+    np.random.seed(seed)
+    x, head, _ = eng.match_features([e.cuda() for e in ref_e], [m.cuda() for m in ref_m], prev_e.cuda(), prev_m.cuda(),
+                                    to_T(cur, eng), K)
+    torch.cuda.synchronize()
+    d = eng.debug
+    O = K + 1
+    pre = from_T(d["pre"])                                                   # [O,24,h,w]
+    names = ["global", "cluster0", "cluster1", "proxy"] + ["local%d" % i for i in range(6)] + \
+            ["locproxy%d" % i for i in range(6)] + ["prev_onehot"] + ["local_bg%d" % i for i in range(6)] + ["global_bg"]
+    worst = 0.0
+    for c, nm in enumerate(names):
+        dd = (pre[:, c] - pre_w[:, c]).abs().max().item()
+        worst = max(worst, dd)
+        print("[parity] match ch%-2d %-12s max|d|=%.3e" % (c, nm, dd))
+    report("attention head", head.view(O, 400).cpu(), head_w, 1e-5)
+    assert worst <= 2e-4, worst
+    # decoder input = [emb x O | prehead]
+    ph = state_dict
+    want_ph = F.relu(F.group_norm(F.conv2d(pre_w, ph["dynamic_prehead.conv.weight"], ph["dynamic_prehead.conv.bias"]), 16,
+                                  ph["dynamic_prehead.bn.weight"], ph["dynamic_prehead.bn.bias"], 1e-5))
+    want_x = torch.cat([cur.expand(O, -1, -1, -1), want_ph], 1)
+    report("decoder input", from_T(x), want_x, 1e-3)
+    eng.keep_debug = False
+
+
+def test_kmeans_vs_restatement(eng):
+    """k-means kernel alone on clustered data: labels bit-exact, centroids 1e-5 vs the numpy restatement of kmeans2."""
+    from oracle.aoc_oracle import kmeans2_points
+    rs = np.random.RandomState(0)
+    h, w, K = 40, 50, 2
+    hw = h * w
+    centers = np.abs(rs.randn(24, 100)).astype(np.float32) * 2
+    x = centers[rs.randint(0, 24, hw)] + 0.3 * rs.randn(hw, 100).astype(np.float32)
+    ids = rs.randint(0, K + 1, hw).astype(np.uint8)
+    emb = torch.from_numpy(x).view(1, h, w, 100).permute(0, 3, 1, 2).contiguous()
+    mask = torch.from_numpy(ids).view(1, 1, h, w)
+    eng.bank.reset()
+    eng.keep_debug = True
+    np.random.seed(11)
+    eng.match_features([emb.cuda()], [mask.cuda()], emb.cuda(), mask.cuda(), to_T(emb, eng), K)
+    torch.cuda.synchronize()
+    d = eng.debug
+    meta = d["meta"]
+    S = d["S"].view(-1, 100).cpu().numpy()
+    np.random.seed(11)
+    for o in range(K + 1):
+        n_o, seg = int(meta[o]), int(meta[16 + o])
+        X = x[ids == o]
+        assert n_o == X.shape[0]
+        assert np.array_equal(S[seg:seg + n_o], X)                 # bank rows: bit-exact gather, raster order
+        cen, lab = kmeans2_points(X, 16, 20)
+        got_lab = d["labels"][seg:seg + n_o].cpu().numpy()
+        got_cen = d["cent"].view(16, 16, 100)[o].cpu().numpy()
+        frac = (got_lab == lab).mean()
+        print("[parity] kmeans obj %d: label agreement %.6f, centroid max|d| %.3e" % (o, frac, np.abs(got_cen - cen).max()))
+        assert frac == 1.0
+        assert np.abs(got_cen - cen).max() < 1e-4
+    eng.keep_debug = False
