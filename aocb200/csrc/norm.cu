@@ -14,12 +14,14 @@ namespace aoc {
 // part layout: [N][S][2][C] doubles (sum, sum of squares).  MASKED: weight = phi[n,p] > thr[n] (strict).
 template <bool MASKED>
 __global__ void __launch_bounds__(256) channel_stats_partial(const float* __restrict__ x, int HW, int C, int ldx,
-                                                              int PB, const float* __restrict__ phi,
+                                                              int PB, int CW, const float* __restrict__ phi,
                                                               const float* __restrict__ thr,
                                                               double* __restrict__ part) {
-    extern __shared__ float sm[];  // [PL][2][C]
+    extern __shared__ float sm[];  // [PL][2][Cc]
     const int n = blockIdx.y, s = blockIdx.x, S = gridDim.x;
-    const int Q = C >> 2;
+    const int c0 = blockIdx.z * CW;            // channel chunk (C > 1024 is processed in chunks of CW channels)
+    const int Cc = min(CW, C - c0);
+    const int Q = Cc >> 2;
     const int PL = 256 / Q;
     const int tid = threadIdx.x;
     const int q = tid % Q, pl = tid / Q;
@@ -31,20 +33,21 @@ __global__ void __launch_bounds__(256) channel_stats_partial(const float* __rest
             if (MASKED) {
                 if (!(__ldg(phi + (size_t)n * HW + p) > th)) continue;
             }
-            float4 v = ldg4(x + ((size_t)n * HW + p) * ldx + q * 4);
+            float4 v = ldg4(x + ((size_t)n * HW + p) * ldx + c0 + q * 4);
             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
             sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y);
             sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
         }
-        float* d = sm + (size_t)pl * 2 * C;
+        float* d = sm + (size_t)pl * 2 * Cc;
         *reinterpret_cast<float4*>(d + q * 4) = sum;
-        *reinterpret_cast<float4*>(d + C + q * 4) = sq;
+        *reinterpret_cast<float4*>(d + Cc + q * 4) = sq;
     }
     __syncthreads();
-    for (int c = tid; c < 2 * C; c += 256) {
+    for (int c = tid; c < 2 * Cc; c += 256) {
         double a = 0.0;
-        for (int l = 0; l < PL; ++l) a += (double)sm[(size_t)l * 2 * C + c];
-        part[((size_t)(n * S + s)) * 2 * C + c] = a;
+        for (int l = 0; l < PL; ++l) a += (double)sm[(size_t)l * 2 * Cc + c];
+        int which = c / Cc, cc = c - which * Cc;
+        part[((size_t)(n * S + s) * 2 + which) * C + c0 + cc] = a;
     }
 }
 
@@ -181,20 +184,21 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
                                      const float* thr, double* stats, void* workspace, size_t ws_bytes,
                                      cudaStream_t stream) {
     AOC_CHECK_ARG(x && stats && workspace, "null pointer");
-    AOC_CHECK_ARG(C % 4 == 0 && C >= 4 && C <= 1024 && ldx % 4 == 0, "C must be a multiple of 4 in [4,1024]");
+    AOC_CHECK_ARG(C % 4 == 0 && C >= 4 && ldx % 4 == 0, "C and ldx must be multiples of 4");
     AOC_CHECK_ARG((((uintptr_t)x) & 15) == 0, "x must be 16-byte aligned");
     AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
     AOC_CHECK_ARG((phi == nullptr) == (thr == nullptr), "phi and thr go together");
     int PB = stats_slab(HW);
     int S = cdiv(HW, PB);
-    int PL = 256 / (C / 4);
-    size_t smem = (size_t)PL * 2 * C * sizeof(float);
-    dim3 grid(S, N);
+    int CW = C < 1024 ? C : 1024;
+    int PL = 256 / (CW / 4);
+    size_t smem = (size_t)PL * 2 * CW * sizeof(float);
+    dim3 grid(S, N, cdiv(C, CW));
     double* part = (double*)workspace;
     if (phi)
-        channel_stats_partial<true><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, phi, thr, part);
+        channel_stats_partial<true><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, CW, phi, thr, part);
     else
-        channel_stats_partial<false><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, nullptr, nullptr, part);
+        channel_stats_partial<false><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, CW, nullptr, nullptr, part);
     dim3 g2(cdiv(2 * C, 256), N);
     channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
     return launch_status("aoc_channel_stats_f32");

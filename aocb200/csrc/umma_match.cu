@@ -1,0 +1,321 @@
+// Pixel-level global matching on the tcgen05 tensor cores (the dominant dense contraction of the path):
+//   for every query pixel and object:  min_n (|q|^2 + |r_n|^2 - 2 q.r_n)   over the object's bank rows,
+// reference: networks/layers/matching.py:2384-2510 (-> :200-249, :63-91, :27-46), 132.85 GFLOP per reference frame
+// at 480p.  The N_q x N_ref distance matrix is never materialised: a CTA owns 128 query rows (TMEM lanes), streams
+// the object-sorted bank through a 6-stage TMA (cp.async.bulk) pipeline, accumulates q.r in TMEM with 3xTF32
+// (fp32-faithful), and the epilogue warps keep one running minimum per thread straight out of tcgen05.ld -- no
+// cross-thread reduction, no chunking (the reference's n_chunks loop disappears).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).  Accumulators are double-buffered in TMEM
+// (2 x 256 columns) so the epilogue of bank block i overlaps the MMAs of block i+1.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace aoc {
+using namespace umma;
+
+constexpr int MAXO_ = AOC_MAX_OBJECTS;
+constexpr int TC_K = 104;              // embedding width 100 zero-padded to a multiple of 8
+constexpr int TC_KS = TC_K / KSTEP;    // 13 k-steps
+constexpr int QB = 128;                // query rows per CTA (= TMEM lanes)
+constexpr int RBK = 256;               // bank rows per MMA (N)
+constexpr int NST = 6;                 // smem pipeline stages (one (row block, k-step) chunk each)
+constexpr uint32_t A_BYTES = TC_KS * 2 * QB * KSTEP * 4;     // 106496
+constexpr uint32_t B_STAGE = 2 * RBK * KSTEP * 4;            // 16384
+constexpr uint32_t SMEM_MATCH = A_BYTES + NST * B_STAGE + 256;
+
+// x [R][ld] fp32 (first K_valid columns used, zero beyond; rows >= R zero) -> tc image with row blocks of RB rows,
+// K = ksteps*8 columns.  One thread per (row, float4 granule).
+__global__ void pack_tc_image_kernel(const float* __restrict__ x, int R, int K_valid, int ld, int RB, int ksteps,
+                                     long long rows_padded, uint8_t* __restrict__ out) {
+    long long total = rows_padded * ksteps * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i % rows_padded;            // consecutive threads -> consecutive rows (coalesced 16 B stores)
+        int g = (int)(i / rows_padded);           // granule index: k = 4*g
+        int ks = g >> 1, half = g & 1;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < R) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int k = g * 4 + e;
+                if (k < K_valid) v[e] = __ldg(x + (size_t)r * ld + k);
+            }
+        }
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[e], lo[e]);
+        long long rb = r / RB;
+        int rr = (int)(r - rb * RB);
+        size_t base = ((size_t)rb * ksteps + ks) * chunk_bytes(RB) + elem_offset(rr, half * 4);
+        *reinterpret_cast<float4*>(out + base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(out + base + block_bytes(RB)) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test)
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restrict__ Qimg,
+                                                          const uint8_t* __restrict__ Simg,
+                                                          const float* __restrict__ q2, const float* __restrict__ r2,
+                                                          const int* __restrict__ meta, int O, int HW, int nrb_total,
+                                                          int nsplit, float* __restrict__ mins, float* __restrict__ C,
+                                                          int ldc, uint32_t lbo, uint32_t sbo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + NST * B_STAGE);
+    // bars: [0..NST) full, [NST..2NST) empty, 2NST = a_full, 2NST+1.. tmem_full[2], 2NST+3.. tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
+    __shared__ int seg[MAXO_ + 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, sp = blockIdx.y;
+    const int rb0 = (int)((long long)nrb_total * sp / nsplit);
+    const int rb1 = (int)((long long)nrb_total * (sp + 1) / nsplit);
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
+    const uint32_t A_FULL = bar0 + 8u * (2 * NST);
+    auto TFULL = [&](int s) { return bar0 + 8u * (2 * NST + 1 + s); };
+    auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + 3 + s); };
+
+    if (threadIdx.x <= O && MODE == 0) seg[threadIdx.x] = meta[MAXO_ + threadIdx.x];
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(A_FULL, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(TFULL(s), 1); mbar_init(TEMPTY(s), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0 && rb1 > rb0) {
+            // ===== TMA producer =====
+            mbar_arrive_expect_tx(A_FULL, A_BYTES);
+            for (int ks = 0; ks < TC_KS; ++ks)
+                bulk_g2s(smem_u32(sA) + ks * (A_BYTES / TC_KS), Qimg + ((size_t)qt * TC_KS + ks) * (A_BYTES / TC_KS),
+                         A_BYTES / TC_KS, A_FULL);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int rb = rb0; rb < rb1; ++rb)
+                for (int ks = 0; ks < TC_KS; ++ks) {
+                    mbar_wait(EMPTY(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(FULL(stage), B_STAGE);
+                    bulk_g2s(smem_u32(sB) + stage * B_STAGE, Simg + ((size_t)rb * TC_KS + ks) * B_STAGE, B_STAGE,
+                             FULL(stage));
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rb1 > rb0) {
+            // ===== MMA issuer (single thread) =====
+            const uint32_t idesc = idesc_tf32(QB, RBK);
+            mbar_wait(A_FULL, 0);
+            tc_fence_after();
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int rb = rb0; rb < rb1; ++rb) {
+                mbar_wait(TEMPTY(as), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)as * RBK;
+                for (int ks = 0; ks < TC_KS; ++ks) {
+                    mbar_wait(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(sA) + ks * (A_BYTES / TC_KS);
+                    const uint32_t a_lo = a_hi + QB * KSTEP * 4;
+                    const uint32_t b_hi = smem_u32(sB) + stage * B_STAGE;
+                    const uint32_t b_lo = b_hi + RBK * KSTEP * 4;
+                    const uint64_t dah = smem_desc(a_hi, lbo, sbo), dal = smem_desc(a_lo, lbo, sbo);
+                    const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
+                    mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                    mma_tf32(d, dah, dbl, idesc, 1u);
+                    mma_tf32(d, dah, dbh, idesc, 1u);
+                    mma_commit(EMPTY(stage));
+                    if (++stage == NST) { stage = 0; phase ^= 1u; }
+                }
+                mma_commit(TFULL(as));
+                as ^= 1;
+                if (as == 0) aphase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 128 threads <-> 128 TMEM lanes (query rows) =====
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const int qi = qt * QB + row;
+        const float qq = (MODE == 0 && qi < HW) ? __ldg(q2 + qi) : 0.f;
+        int as = 0;
+        uint32_t aphase = 0;
+        int cur = 0;
+        float m = INFINITY;
+        if (MODE == 0) {
+            while (cur < O - 1 && rb0 * RBK >= seg[cur + 1]) ++cur;
+        }
+        for (int rb = rb0; rb < rb1; ++rb) {
+            if (MODE == 0) {
+                if (rb * RBK >= seg[cur + 1]) {   // crossed into the next object's segment: flush
+                    if (qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = m;
+                    m = INFINITY;
+                    while (cur < O - 1 && rb * RBK >= seg[cur + 1]) ++cur;
+                }
+            }
+            mbar_wait(TFULL(as), aphase);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * RBK;
+#pragma unroll 1
+            for (int c0 = 0; c0 < RBK; c0 += 32) {
+                float v[32];
+                tmem_ld32(t0 + c0, v);
+                tmem_ld_wait();
+                if (MODE == 0) {
+                    const float4* rr = reinterpret_cast<const float4*>(r2 + (size_t)rb * RBK + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 r4 = __ldg(rr + j4);
+                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 0], qq + r4.x));   // (|q|^2+|r|^2) - 2 q.r  (matching.py:45)
+                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 1], qq + r4.y));
+                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 2], qq + r4.z));
+                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 3], qq + r4.w));
+                    }
+                } else {
+                    float* dst = C + (size_t)qi * ldc + (size_t)rb * RBK + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(TEMPTY(as));
+            as ^= 1;
+            if (as == 0) aphase ^= 1u;
+        }
+        if (MODE == 0 && rb1 > rb0 && qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = m;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// mins[split][HW][O] -> min over splits, in place into split 0
+__global__ void min_over_splits_kernel(float* __restrict__ mins, long long n, int nsplit) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = mins[i];
+    for (int s = 1; s < nsplit; ++s) m = fminf(m, mins[(size_t)s * n + i]);
+    mins[i] = m;
+}
+
+static int pick_splits(int nqt, int nrb) {
+    int s = 1;
+    while (nqt * s < 2 * 148 && s * 2 <= nrb && s < 16) s *= 2;
+    return s;
+}
+
+static bool g_attr0 = false, g_attr1 = false;
+
+}  // namespace aoc
+
+using namespace aoc;
+
+extern "C" size_t aoc_tc_image_bytes(long long rows, int K_img, int RB) {
+    long long rb = (rows + RB - 1) / RB;
+    int ks = (K_img + KSTEP - 1) / KSTEP;
+    return (size_t)rb * ks * chunk_bytes(RB);
+}
+
+// x [rows][ld] (first K columns valid) -> tc image with K_img >= K columns (zero padded), row blocks of RB rows
+extern "C" int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int ld, int RB, int K_img, void* out,
+                                     cudaStream_t stream) {
+    AOC_CHECK_ARG(x && out && rows > 0 && K > 0 && K_img >= K, "bad args");
+    AOC_CHECK_ARG(RB % 8 == 0 && RB >= 8, "RB must be a multiple of 8");
+    int ks = (K_img + KSTEP - 1) / KSTEP;
+    long long rows_padded = (rows + RB - 1) / RB * RB;
+    long long total = rows_padded * ks * 2;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, K, ld, RB, ks, rows_padded, (uint8_t*)out);
+    return launch_status("aoc_pack_tc_image_f32");
+}
+
+extern "C" size_t aoc_global_match_tc_workspace_bytes(int HW) {
+    // query image (RB=128) + |q|^2 + mins[16 splits][HW][MAXO]
+    size_t img = aoc_tc_image_bytes(HW, TC_K, QB);
+    return img + (size_t)(HW + QB) * sizeof(float) + (size_t)16 * HW * MAXO_ * sizeof(float) + 1024;
+}
+
+// q [HW][100]; S_tc = tc image (RB=256) of the sorted bank rows (aoc_pack_tc_image_f32 of S), r2 = |row|^2 (+inf pad);
+// meta (device) as written by aoc_bank_index_build with align = 256; rows_padded = meta[2*MAXO+1] (host copy).
+extern "C" int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev,
+                                   int rows_padded, const float* bias, int O, void* workspace, size_t ws_bytes,
+                                   float* out, cudaStream_t stream) {
+    AOC_CHECK_ARG(q && S_tc && r2 && meta_dev && bias && workspace && out, "null pointer");
+    AOC_CHECK_ARG(O >= 1 && O <= MAXO_ && HW > 0 && rows_padded % RBK == 0, "bad dims");
+    AOC_CHECK_ARG(ws_bytes >= aoc_global_match_tc_workspace_bytes(HW), "workspace too small");
+    uint8_t* ws = (uint8_t*)workspace;
+    size_t img = aoc_tc_image_bytes(HW, TC_K, QB);
+    uint8_t* Qimg = ws;
+    float* q2 = (float*)(ws + img);
+    float* mins = q2 + (HW + QB);
+    int nqt = cdiv(HW, QB), nrb = rows_padded / RBK;
+    int rc = aoc_pack_tc_image_f32(q, HW, 100, 100, QB, TC_K, Qimg, stream);
+    if (rc) return rc;
+    rc = aoc_row_sqnorm_f32(q, HW, q2, stream);
+    if (rc) return rc;
+    int nsplit = nrb > 0 ? pick_splits(nqt, nrb) : 1;
+    long long n = (long long)HW * O;
+    fill_f32_kernel<<<cdiv(n * nsplit, 1024), 256, 0, stream>>>(mins, INFINITY, n * nsplit);
+    if (nrb > 0) {
+        if (!g_attr0) {
+            cudaFuncSetAttribute(match_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
+            g_attr0 = true;
+        }
+        dim3 grid(nqt, nsplit);
+        match_tc_kernel<0><<<grid, 256, SMEM_MATCH, stream>>>(Qimg, (const uint8_t*)S_tc, q2, r2, meta_dev, O, HW, nrb,
+                                                             nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
+        if (nsplit > 1) min_over_splits_kernel<<<cdiv(n, 256), 256, 0, stream>>>(mins, n, nsplit);
+    }
+    rc = aoc_global_match_finalize_f32(mins, meta_dev, bias, HW, O, out, stream);
+    if (rc) return rc;
+    return launch_status("aoc_global_match_tc");
+}
+
+// Self-test of the tcgen05 pipeline: C[M][N] = A[M][K] * B[N][K]^T, K <= 104 (zero padded), M % 128 == 0, N % 256 == 0.
+// variant 0: descriptors as designed; variant 1: LBO/SBO swapped (diagnostic only).  ws: packed images.
+extern "C" int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, int M, int N, int K, int variant,
+                                    void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    AOC_CHECK_ARG(A && B && C && workspace, "null pointer");
+    AOC_CHECK_ARG(M % QB == 0 && N % RBK == 0 && K > 0 && K <= TC_K, "M%128, N%256, K<=104 required");
+    size_t ia = aoc_tc_image_bytes(M, TC_K, QB), ib = aoc_tc_image_bytes(N, TC_K, RBK);
+    AOC_CHECK_ARG(ws_bytes >= ia + ib, "workspace too small");
+    uint8_t* Ai = (uint8_t*)workspace;
+    uint8_t* Bi = Ai + ia;
+    int rc = aoc_pack_tc_image_f32(A, M, K, K, QB, TC_K, Ai, stream);
+    if (rc) return rc;
+    rc = aoc_pack_tc_image_f32(B, N, K, K, RBK, TC_K, Bi, stream);
+    if (rc) return rc;
+    if (!g_attr1) {
+        cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
+        g_attr1 = true;
+    }
+    dim3 grid(M / QB, 1);
+    uint32_t lbo = variant == 1 ? SBO_BYTES : LBO_BYTES, sbo = variant == 1 ? LBO_BYTES : SBO_BYTES;
+    match_tc_kernel<1><<<grid, 256, SMEM_MATCH, stream>>>(Ai, Bi, nullptr, nullptr, nullptr, 1, M, N / RBK, 1, nullptr, C,
+                                                         N, lbo, sbo);
+    return launch_status("aoc_gemm_tf32x3_test");
+}

@@ -5,6 +5,8 @@ for device memory, the current stream and a few index/dtype conversions on label
 AOCNet.forward_for_eval / before_seghead_process (networks/aoc/aocnet.py:84-372) and CalibrationDecoding.forward
 (networks/aoc/decoding_module.py:96-225) of the reference, with SURVEY.md Appendix A's repair set.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -139,6 +141,11 @@ class Engine:
         self.cluster_num = 16
         self.debug = {}
         self.keep_debug = False
+        # tensor-core (tcgen05, 3xTF32) kernels vs the fp32 SIMT kernels; both are CUDA, same results to ~1e-6 relative
+        tc = os.environ.get("AOCB200_TC", "1") != "0"
+        self.tc_conv = tc
+        self.tc_match = tc
+        self._wpacked = {}
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self._ws = {}
 
@@ -170,6 +177,18 @@ class Engine:
         if out is None:
             out = self.new(x.N, Ho, Wo, Cout)
         assert out.C == Cout and out.H == Ho and out.W == Wo and out.N == x.N
+        if self.tc_conv and Cin % 4 == 0 and x.ld % 4 == 0:
+            wp = self._wpacked.get(name)
+            if wp is None or wp[0] is not w:
+                K = kh * kw * Cin
+                buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, K), dtype=torch.uint8, device=self.dev)
+                self.L.conv_pack_weights_tf32x3(w.data_ptr(), Cout, K, buf.data_ptr(), self.stream)
+                wp = (w, buf)
+                self._wpacked[name] = wp
+            self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
+                                  out.ptr, x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw,
+                                  stride, pad, dil, 1 if relu else 0, self.stream)
+            return out
         self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
                                x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw, stride,
                                pad, dil, 1 if relu else 0, self.stream)
@@ -374,9 +393,17 @@ class Engine:
         L.bank_gather_f32(bk.emb_all.data_ptr(), row_src.data_ptr(), rows, S.data_ptr(), r2.data_ptr(), st)
         # --- pixel-level global matching (matching.py:2384)
         g = self.empty(hw * O)
-        mins = self.empty(hw * O)
-        L.global_match_simt_f32(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), bias.data_ptr(), O,
-                                mins.data_ptr(), g.data_ptr(), st)
+        if self.tc_match and rows > 0:
+            nimg = L.tc_image_bytes(rows, 104, 256)
+            S_tc = self.ws("bank_tc", nimg)
+            L.pack_tc_image_f32(S.data_ptr(), rows, EMB, EMB, 256, 104, S_tc.data_ptr(), st)
+            nws2 = L.global_match_tc_workspace_bytes(hw)
+            L.global_match_tc(q.ptr, hw, S_tc.data_ptr(), r2.data_ptr(), meta.data_ptr(), rows, bias.data_ptr(), O,
+                              self.ws("gm_tc", nws2).data_ptr(), nws2, g.data_ptr(), st)
+        else:
+            mins = self.empty(hw * O)
+            L.global_match_simt_f32(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), bias.data_ptr(), O,
+                                    mins.data_ptr(), g.data_ptr(), st)
         # --- adaptive object proxies (matching.py:533-595): k chain + init rows from numpy's global RNG
         kk = np.zeros(MAXO, dtype=np.int32)
         init = np.zeros((MAXO, 16), dtype=np.int32)

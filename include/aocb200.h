@@ -122,18 +122,22 @@ size_t aoc_bank_workspace_bytes(int total_pixels, int O);
 int aoc_bank_index_build(const uint8_t* ids, int total_pixels, int O, int align, int* meta_out, int* row_src,
                          int cap_rows, int* nat2sorted, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int aoc_bank_gather_f32(const float* emb_all, const int* row_src, int rows, float* S, float* r2, cudaStream_t stream);
-/* tcgen05 operand image of the same rows (3xTF32 hi/lo split, K-chunked core-matrix layout) */
-size_t aoc_bank_tc_bytes(int rows);
-int aoc_bank_gather_tc(const float* emb_all, const int* row_src, int rows, void* S_tc, float* r2, cudaStream_t stream);
+/* tcgen05 operand image ("tc image", see csrc/umma.cuh): 3xTF32 hi/lo split of x[rows][K] in the K-major core-matrix
+ * layout, row blocks of RB rows, K zero-padded to K_img (multiple of 8).  Used for the sorted bank (RB = 256,
+ * K_img = 104) and consumed by TMA bulk copies without further transformation. */
+size_t aoc_tc_image_bytes(long long rows, int K_img, int RB);
+int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int ld, int RB, int K_img, void* out,
+                          cudaStream_t stream);
 
 /* ---------------------------------------------------------------- matching (matching.cu, umma_match.cu) */
 /* global_matching_for_eval (matching.py:2384-2510): out [HW][O] */
 int aoc_global_match_simt_f32(const float* q, int HW, const float* S, const float* r2, const int* meta,
                               const float* bias, int O, float* mins_ws, float* out, cudaStream_t stream);
-int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev,
-                        const int* meta_host, const float* bias, int O, void* q_tc_ws, float* mins_ws, float* out,
-                        cudaStream_t stream);
+/* Same result on the tcgen05 tensor cores (3xTF32, TMEM accumulators, TMA-fed): S_tc = tc image (RB = 256,
+ * K_img = 104) of the sorted bank built with align = 256; rows_padded = meta[2*AOC_MAX_OBJECTS+1]. */
 size_t aoc_global_match_tc_workspace_bytes(int HW);
+int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev, int rows_padded,
+                        const float* bias, int O, void* workspace, size_t ws_bytes, float* out, cudaStream_t stream);
 int aoc_global_match_finalize_f32(const float* mins, const int* meta, const float* bias, int HW, int O, float* out,
                                   cudaStream_t stream);
 /* cluster level (matching.py:602-637) and k=1 proxy level (matching.py:149-197): out_cluster [HW][O][2], out_proxy [HW][O] */
@@ -167,9 +171,10 @@ int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8_t* label, 
                              cudaStream_t stream);
 
 /* ---------------------------------------------------------------- tcgen05 self-test (umma_gemm.cu) */
-/* C[M][N] = A[M][K] * B[N][K]^T with the 3xTF32 tcgen05 pipeline (M%128==0, N%128==0, K%8==0); test hook. */
-int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, int M, int N, int K, int variant,
-                         cudaStream_t stream);
+/* C[M][N] = A[M][K] * B[N][K]^T through the same tcgen05 pipeline as aoc_global_match_tc (M%128==0, N%256==0,
+ * K<=104); workspace >= tc images of A (RB 128) and B (RB 256).  variant 1 swaps LBO/SBO (diagnostic). */
+int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, int M, int N, int K, int variant, void* workspace,
+                         size_t ws_bytes, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

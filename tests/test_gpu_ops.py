@@ -13,7 +13,9 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def eng(state_dict):
     from aocb200.engine import Engine
-    return Engine(state_dict, torch.device("cuda:0"))
+    e = Engine(state_dict, torch.device("cuda:0"))
+    e.tc_conv = e.tc_match = False        # fp32 SIMT kernels here; tests/test_gpu_tc.py covers the tcgen05 kernels
+    return e
 
 
 def _conv_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu, res, scale, bias, ld_in=None, off_in=0, seed=0):
@@ -167,7 +169,8 @@ def test_resize(eng):
 
 def _rand_scene(seed, h, w, K, F_, absent=None, with125=True):
     g = torch.Generator().manual_seed(seed)
-    embs = [F.relu(torch.randn(1, 100, h, w, generator=g)) for _ in range(F_ + 2)]
+    base = F.relu(torch.randn(K + 1, 100, generator=g)) * 0.15
+    embs = []
     H, W = 4 * (h - 1) + 1, 4 * (w - 1) + 1
     masks = []
     for i in range(F_ + 1):
@@ -178,6 +181,10 @@ def _rand_scene(seed, h, w, K, F_, absent=None, with125=True):
         if with125 and i > 0:
             m[:, :, : H // 5, : W // 3] = 125
         masks.append(m)
+    for i in range(F_ + 2):   # embeddings correlated with the labels, O(1) squared distances (sigmoid not saturated)
+        lab = F.interpolate(masks[min(i, F_)].float(), size=(h, w), mode="nearest").long().clamp(0, K)[0, 0]
+        e = base[lab].permute(2, 0, 1)[None] + 0.05 * torch.randn(1, 100, h, w, generator=g)
+        embs.append(F.relu(e))
     return embs, masks, (H, W)
 
 
