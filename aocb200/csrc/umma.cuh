@@ -8,8 +8,8 @@
 //   layout: core matrix = 8 rows x 16 bytes stored contiguously (128 B);
 //       byte offset(r, k) = (r / 8) * 256 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4
 //   i.e. SBO (8-row group stride) = 256 B, LBO (k-chunk stride) = 128 B.
-//   hi = x with the low 13 mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32); the product is
-//   evaluated as lo*hi' + hi*lo' + hi*hi' with fp32 accumulation in TMEM (3xTF32; the lo*lo' term ~2^-22 is dropped).
+//   hi = rna_tf32(x), lo = rna_tf32(x - hi); the product is evaluated as lo*hi' + hi*lo' + hi*hi' with fp32
+//   accumulation in TMEM (3xTF32; the lo*lo' term ~2^-22 is dropped).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,9 +29,15 @@ __host__ __device__ inline uint32_t elem_offset(int r, int k) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// x = hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi): both exactly representable in TF32 (low 13 mantissa
+// bits zero), so the tensor core's operand conversion is a no-op and the residual errors (lo*lo' dropped, rounding of
+// lo) are zero-mean ~2^-22 relative per product instead of a truncation bias.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    lo = x - hi;
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
 }
 
 // ---------------------------------------------------------------- mbarrier

@@ -46,13 +46,24 @@ class AocError(RuntimeError):
     pass
 
 
+# CUDA kernels launched by one call of each entry point (everything else launches exactly one); used for the
+# `gpu_launches` figure of bench.py.  aoc_kmeans_proxies_f32 launches 1 + 2*iters + 2 (counted by the caller).
+KERNELS_PER_CALL = {
+    "aoc_channel_stats_f32": 2, "aoc_bank_index_build": 4, "aoc_global_match_simt_f32": 2, "aoc_global_match_tc": 6,
+    "aoc_head_pool_f32": 2, "aoc_dyn_logits_f32": 2, "aoc_gemm_tf32x3_test": 3,
+    "aoc_version": 0, "aoc_check_device": 0, "aoc_last_error_string": 0,
+}
+
+
 class _Lib:
     def __init__(self):
         if not os.path.exists(LIB_PATH):
             raise AocError("libaocb200.so is not built (run `python -m aocb200.build`); there is no fallback path")
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
-        self.launches = 0
+        self.launches = 0          # kernels launched through this binding (see KERNELS_PER_CALL)
+        self.calls = 0
+        self.profile = None        # {entry point name: [(start_event, end_event, args), ...]} when profiling
         for name, (ret, args) in self.protos.items():
             fn = getattr(self.cdll, name)
             fn.restype = _ctype(ret) if ret != "int" else ctypes.c_int
@@ -63,11 +74,28 @@ class _Lib:
                 setattr(self, name[4:], fn)
 
     def _checked(self, fn, name):
+        per_call = KERNELS_PER_CALL.get(name, 1)
+        is_query = name.endswith("_bytes")
+
         def call(*a):
-            rc = fn(*a)
+            prof = self.profile
+            if prof is not None and name in prof:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*a)
+                e1.record()
+                prof[name].append((e0, e1, a))
+            else:
+                rc = fn(*a)
             if rc != 0:
                 raise AocError("%s failed (%d): %s" % (name, rc, self.cdll.aoc_last_error_string().decode()))
-            self.launches += 1
+            if not is_query:
+                self.calls += 1
+                if name == "aoc_kmeans_proxies_f32":
+                    self.launches += 3 + 2 * a[7]
+                else:
+                    self.launches += per_call
             return rc
         return call
 

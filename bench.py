@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the AOC-Net per-frame inference path (BASELINE.json: 480p 5-object VOS frames/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one predicted frame of a synthetic YouTube-VOS-shaped 480p clip with 5 objects (BASELINE.json configs[2];
+one independent clip per GPU, sharded with no collective on the per-frame path): backbone + global/cluster/proxy/local
+matching (k-means proxies, memory bank growing every 5 frames) + calibration decoder + softmax, driven through the
+reference-facing API `get_module() -> forward_for_eval` by the eval-loop mirror in aocb200/sequence.py.
+
+value  : frames/s with the clip's frames already resident in HBM (CUDA events, max over ranks).
+e2e    : same, but every step copies its frame from pinned host memory (H2D) and reads the predicted label map
+         back (D2H) inside the timed region.
+roofline / cpu_baseline: see DESIGN.md ("Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H480, W480, K_OBJ = 480, 854, 5          # source resolution; MultiRestrictSize -> 481 x 849
+MEM_EVERY = 5
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"], "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_workload(seed, n_frames):
+    from aocb200.synth import make_clip, restrict_size
+    H, W = restrict_size(H480, W480)
+    frames, labels = make_clip(seed, H, W, K_OBJ, n_frames)
+    return frames, labels[0], (H, W)
+
+
+class Stepper:
+    """The eval loop of aocb200/sequence.py unrolled into explicit steps (so that exactly K of them can be timed)."""
+
+    def __init__(self, model, frames, first_label, K, device, host_io):
+        from aocb200.sequence import shannon_entropy
+        self.ent = shannon_entropy
+        self.m, self.K, self.dev, self.host_io = model, K, device, host_io
+        self.T, _, self.H, self.W = frames.shape
+        self.frames = frames.pin_memory() if host_io else frames.to(device)
+        self.gt_ids = torch.tensor([K], device=device)
+        self.ref_e, self.ref_m = [], []
+        self.memory = [[None, None]]
+        self.t = 0
+        self.out_host = torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory() if host_io else None
+        img = self.frames[0:1].to(device, non_blocking=True)
+        _, emb, self.memory = model.forward_for_eval(self.memory, self.ref_e, self.ref_m, None, None, img,
+                                                     pred_size=[self.H, self.W], gt_ids=self.gt_ids)
+        lab = first_label.to(device).view(1, 1, self.H, self.W)
+        self.ref_e.append(emb); self.ref_m.append(lab)
+        self.prev_e, self.prev_m = emb, lab
+        self.h2d = 0
+        self.d2h = 0
+
+    def step(self):
+        self.t += 1
+        t = self.t
+        img = self.frames[t:t + 1].to(self.dev, non_blocking=True)
+        if self.host_io:
+            self.h2d += img.numel() * 4
+        probs, emb, self.memory = self.m.forward_for_eval(self.memory, self.ref_e, self.ref_m, self.prev_e, self.prev_m,
+                                                          img, pred_size=[self.H, self.W], gt_ids=self.gt_ids)
+        pred = torch.argmax(probs[0], dim=0)
+        cur = pred.view(1, 1, self.H, self.W)
+        if t % MEM_EVERY == 0:                                   # eval_manager_mm.py:309-312,:339-361
+            unc = self.ent(probs)[0, 0]
+            region = (unc > 1.0).long()
+            conf = (pred * (1 - region) + 125 * region).view(1, 1, self.H, self.W)
+            self.ref_e.append(emb); self.ref_m.append(conf)
+        self.prev_e, self.prev_m = emb, cur
+        if self.host_io:
+            self.out_host.copy_(pred.to(torch.uint8), non_blocking=True)
+            self.d2h += self.out_host.numel()
+            torch.cuda.current_stream().synchronize()            # the caller consumes the mask of this frame
+        return pred
+
+
+def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sampler=None):
+    np.random.seed(1000 + (dist.get_rank() if dist else 0))
+    st = Stepper(model, frames, first, K_OBJ, device, host_io)
+    for _ in range(warmup):
+        st.step()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.h2d = st.d2h = 0
+    from aocb200.lib import lib
+    l0 = lib().launches
+    e0.record()
+    for _ in range(steps):
+        st.step()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms, st, lib().launches - l0, clocks
+
+
+def kernel_profile(model, frames, first, device, n_frames):
+    """CUDA-event duration of every launch of the two tensor-core kernels over `n_frames` predicted frames."""
+    from aocb200.lib import lib
+    L = lib()
+    np.random.seed(77)
+    st = Stepper(model, frames, first, K_OBJ, device, False)
+    for _ in range(2):
+        st.step()
+    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_kmeans_proxies_f32": []}
+    for _ in range(n_frames):
+        st.step()
+    torch.cuda.synchronize()
+    prof, L.profile = L.profile, None
+    out = {}
+    conv = prof["aoc_conv2d_nhwc_tc"]
+    if conv:
+        fl, ms = 0.0, 0.0
+        for e0, e1, a in conv:
+            N, H, W, Cin, Cout, kh, kw, stride, pad, dil = a[6], a[7], a[8], a[9], a[11], a[14], a[15], a[16], a[17], a[18]
+            Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+            Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+            fl += 2.0 * N * Ho * Wo * Cout * kh * kw * Cin
+            ms += e0.elapsed_time(e1)
+        out["conv"] = {"launches": len(conv), "ms": ms, "flop": fl}
+    gm = prof["aoc_global_match_tc"]
+    if gm:
+        fl, ms = 0.0, 0.0
+        for e0, e1, a in gm:
+            fl += 2.0 * a[1] * a[5] * 100        # HW x (padded) bank rows x C
+            ms += e0.elapsed_time(e1)
+        out["match"] = {"launches": len(gm), "ms": ms, "flop": fl}
+    km = prof["aoc_kmeans_proxies_f32"]
+    if km:
+        ms = sum(e0.elapsed_time(e1) for e0, e1, a in km)
+        out["kmeans"] = {"launches": len(km), "ms": ms}
+    out["frames"] = n_frames
+    return out
+
+
+def cpu_baseline(frames, first, n_timed):
+    """The reference algorithm (oracle port, fp32 torch-on-CPU + scipy) on the host cores: predicted frames/s."""
+    from aocb200.params import synthetic_state_dict
+    from oracle.aoc_oracle import AOCOracle
+    torch.set_num_threads(os.cpu_count())
+    orc = AOCOracle(synthetic_state_dict(1234))
+    H, W = frames.shape[2:]
+    gt = torch.tensor([K_OBJ])
+    np.random.seed(1000)
+    with torch.no_grad():
+        _, emb, mem = orc.forward_for_eval([[None, None]], [], [], None, None, frames[0:1], [H, W], gt)
+        lab = first.view(1, 1, H, W)
+        ref_e, ref_m, prev_e, prev_m = [emb], [lab], emb, lab
+        t0 = time.perf_counter()
+        for t in range(1, n_timed + 1):
+            probs, emb, mem = orc.forward_for_eval(mem, ref_e, ref_m, prev_e, prev_m, frames[t:t + 1], [H, W], gt)
+            prev_e, prev_m = emb, torch.argmax(probs[0], 0).view(1, 1, H, W)
+        dt = time.perf_counter() - t0
+    return n_timed / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=26)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=2, help="predicted frames timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    H, W = 481, 849
+    config = {"workload": "synthetic YouTube-VOS-shaped 480p clip (480x854 -> %dx%d), %d objects, 1 GT frame + %d warm-up + "
+                          "%d timed predicted frames, memory bank +1 frame every %d, one independent clip per GPU"
+                          % (H, W, K_OBJ, args.warmup, args.steps, MEM_EVERY),
+              "l2": "no flush: per-step working set (>300 MB of activations + bank) exceeds the 126 MB L2",
+              "precision": "fp32 I/O; tensor-core kernels use 3xTF32 (fp32-faithful), fp32 accumulate"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = max(2, min(args.steps, 6))
+        frames, first, _ = make_workload(0, n + 1)
+        fps, dt = cpu_baseline(frames, first, n)
+        line = {"impl": "reference", "metric": "480p 5-object VOS frames/sec", "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": 1000.0 * dt / n, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "%d predicted frames of the same clip after the GT frame (oracle port of the "
+                                           "reference forward, torch CPU fp32 + scipy kmeans2)" % n},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from aocb200.model import get_module
+    from aocb200.params import synthetic_state_dict
+    from aocb200.shard import broadcast_state_dict
+    model = get_module()(None, None)
+    model.load_state_dict(synthetic_state_dict(1234))
+    model = model.cuda(local).eval()
+    if dist:
+        broadcast_state_dict(model.state_dict(), 0, device)     # the only collective: weights at init
+        model._engine = None
+    n_frames = 1 + args.warmup + args.steps
+    frames, first, _ = make_workload(rank, n_frames)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, st, launches, clocks = timed_run(model, frames, first, device, args.steps, args.warmup, False, dist, sampler)
+    ms_e2e, st2, _, _ = timed_run(model, frames, first, device, args.steps, args.warmup, True, dist)
+    value = world * args.steps / (ms / 1000.0)
+    e2e = world * args.steps / (ms_e2e / 1000.0)
+
+    line = {"metric": "480p 5-object VOS frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": st2.h2d // args.steps,
+                    "d2h_bytes_per_step": st2.d2h // args.steps},
+            "gpu_launches": launches, "clocks": clocks}
+    if rank == 0:
+        pk = peaks()
+        prof = kernel_profile(model, frames, first, device, min(6, args.steps))
+        step_ms = ms / args.steps
+        roofs = {}
+        for key, nm in (("conv", "conv_tc_kernel (tcgen05 implicit-GEMM conv, 3xTF32)"),
+                        ("match", "match_tc_kernel (tcgen05 global matching, 3xTF32)")):
+            if key in prof:
+                p = prof[key]
+                ach = p["flop"] / (p["ms"] * 1e-3) / 1e12
+                roofs[key] = {"kernel": nm, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
+                              "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 dense, sustained",
+                              "launches_per_step": p["launches"] / prof["frames"],
+                              "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
+                              "note": "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 TF32 MMAs per "
+                                      "product (exact mode), so its hardware ceiling is peak/6"}
+        dom = max(roofs.values(), key=lambda r: r["ms_per_step"]) if roofs else None
+        line["roofline"] = dom
+        line["roofline_all"] = roofs
+        if "kmeans" in prof:
+            line["kmeans_ms_per_step"] = prof["kmeans"]["ms"] / prof["frames"]
+        if world == 1 and not args.no_cpu_baseline:
+            fps, dt = cpu_baseline(frames.cpu(), first, args.cpu_frames)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "%d predicted frames of the same clip after the GT frame (oracle port of "
+                                              "the reference forward, torch CPU fp32 + scipy kmeans2), %.1f s"
+                                              % (args.cpu_frames, dt)}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,7 +18,8 @@ def eng(state_dict):
     return e
 
 
-def _conv_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu, res, scale, bias, ld_in=None, off_in=0, seed=0):
+def _conv_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu, res, scale, bias, ld_in=None, off_in=0, seed=0,
+               tolmul=1.0):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
@@ -40,7 +41,7 @@ def _conv_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu, res, scale, b
              in_scale=None if sc is None else sc.cuda().contiguous(), out=out)
     torch.cuda.synchronize()
     report("conv %dx%d s%d d%d %d->%d M=%d" % (k, k, stride, dil, Cin, Cout, N * want.shape[2] * want.shape[3]),
-           from_T(out), want, 2e-5 * max(1.0, want.abs().max().item()))
+           from_T(out), want, tolmul * 2e-5 * max(1.0, want.abs().max().item()))
 
 
 def test_conv2d(eng):

@@ -32,25 +32,25 @@ def test_gemm_tf32x3(eng):
         res[variant] = err
         print("[parity] tcgen05 3xTF32 gemm variant %d: max|d|=%.3e (|C| max %.2f; fp32 matmul err %.3e)" %
               (variant, err, want.abs().max().item(), (A @ B.t()).double().sub(want).abs().max().item()))
-    assert res[0] < 5e-5, res
+    assert res[0] < 2e-5, res
 
 
 def test_conv_tc_vs_torch(eng):
     from test_gpu_ops import _conv_case
     eng.tc_conv = True
     try:
-        _conv_case(eng, 1, 33, 41, 4, 64, 7, 2, 3, 1, True, False, False, True, seed=101)
-        _conv_case(eng, 1, 17, 23, 64, 256, 1, 1, 0, 1, True, True, False, True, seed=102)
-        _conv_case(eng, 1, 17, 23, 128, 128, 3, 2, 1, 1, True, False, False, True, seed=103)
-        _conv_case(eng, 1, 9, 13, 512, 512, 3, 1, 4, 4, True, False, False, True, seed=104)
-        _conv_case(eng, 3, 19, 21, 164, 64, 1, 1, 0, 1, False, False, True, False, seed=105)
-        _conv_case(eng, 2, 19, 21, 256, 100, 1, 1, 0, 1, False, False, False, True, seed=106)
-        _conv_case(eng, 2, 13, 17, 24, 64, 1, 1, 0, 1, False, False, False, True, seed=107)
-        _conv_case(eng, 6, 61, 107, 320, 128, 3, 1, 1, 1, False, False, False, False, seed=108)
-        _conv_case(eng, 2, 1, 1, 512, 128, 1, 1, 0, 1, True, False, False, False, seed=109)
-        _conv_case(eng, 2, 12, 14, 48, 64, 3, 1, 6, 6, False, False, True, False, ld_in=80, off_in=16, seed=110)
-        _conv_case(eng, 1, 61, 107, 2048, 256, 3, 1, 6, 6, True, False, False, True, seed=111)
-        _conv_case(eng, 6, 61, 107, 256, 512, 1, 1, 0, 1, False, False, False, False, seed=112)
+        _conv_case(eng, 1, 33, 41, 4, 64, 7, 2, 3, 1, True, False, False, True, seed=101, tolmul=3.0)
+        _conv_case(eng, 1, 17, 23, 64, 256, 1, 1, 0, 1, True, True, False, True, seed=102, tolmul=3.0)
+        _conv_case(eng, 1, 17, 23, 128, 128, 3, 2, 1, 1, True, False, False, True, seed=103, tolmul=3.0)
+        _conv_case(eng, 1, 9, 13, 512, 512, 3, 1, 4, 4, True, False, False, True, seed=104, tolmul=3.0)
+        _conv_case(eng, 3, 19, 21, 164, 64, 1, 1, 0, 1, False, False, True, False, seed=105, tolmul=3.0)
+        _conv_case(eng, 2, 19, 21, 256, 100, 1, 1, 0, 1, False, False, False, True, seed=106, tolmul=3.0)
+        _conv_case(eng, 2, 13, 17, 24, 64, 1, 1, 0, 1, False, False, False, True, seed=107, tolmul=3.0)
+        _conv_case(eng, 6, 61, 107, 320, 128, 3, 1, 1, 1, False, False, False, False, seed=108, tolmul=3.0)
+        _conv_case(eng, 2, 1, 1, 512, 128, 1, 1, 0, 1, True, False, False, False, seed=109, tolmul=3.0)
+        _conv_case(eng, 2, 12, 14, 48, 64, 3, 1, 6, 6, False, False, True, False, ld_in=80, off_in=16, seed=110, tolmul=3.0)
+        _conv_case(eng, 1, 61, 107, 2048, 256, 3, 1, 6, 6, True, False, False, True, seed=111, tolmul=3.0)
+        _conv_case(eng, 6, 61, 107, 256, 512, 1, 1, 0, 1, False, False, False, False, seed=112, tolmul=3.0)
     finally:
         eng.tc_conv = True
 
@@ -71,4 +71,4 @@ def test_global_match_tc_vs_simt(eng):
             outs[tc] = eng.debug["g"].clone().cpu()
         eng.keep_debug = False
         eng.tc_match = True
-        report("global match tcgen05 vs simt (seed %d)" % seed, outs[True], outs[False], 2e-6)
+        report("global match tcgen05 vs simt (seed %d)" % seed, outs[True], outs[False], 5e-6)

@@ -11,7 +11,8 @@ from aocb200.sequence import run_sequence
 from aocb200.synth import make_clip
 from oracle.aoc_oracle import AOCOracle, kmeans2_points
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.pt")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tiny_*.pt"))
+              if not p.endswith("_fp64.pt"))
 
 
 class Hooked:
