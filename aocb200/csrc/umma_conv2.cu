@@ -1,0 +1,480 @@
+// Implicit-GEMM convolution on the tcgen05 tensor cores, second generation (NHWC fp32 activations, fp32-faithful).
+//   y[m, co] = sum_k A[m, k] * W[co, k],   m = (n, ho, wo) in a th x tw pixel patch,  k = (r, s, ci)
+// Replaces the cuDNN nn.Conv2d call sites of the ResNet101-DeepLabv3+ backbone and the calibration decoder
+// (resnet.py:23-42, deeplab/aspp.py:62-74, deeplab/decoder.py:32-41, layers/gct.py:68-91, layers/aspp.py:57-70,
+// decoding_module.py:162-190,228-240), with the per-(sample, channel) affine that precedes them in the reference
+// (GroupNorm apply + ReLU, GCT / IA gate) fused into the operand path.
+//
+// Data flow of one CTA (128 output pixels x TN output channels, K consumed in stages of 16 input channels of one tap):
+//   warp 12  TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][16] (zero fill = conv padding,
+//            element strides = conv stride, 64B swizzle) into an 8-deep ring
+//   warps 0-3  transform: raw -> (optional a*x+b, ReLU, padding mask) -> 3xTF32 split hi = rna(x), lo = rna(x - hi)
+//            -> tcgen05 K-major core-matrix layout in the 4-deep operand ring (generic proxy -> fence.proxy.async)
+//   warp 13  TMA bulk copies of the pre-split weight image into the same operand ring stage
+//   warp 14  one thread issues tcgen05.mma kind::tf32:  hi*hi -> MAIN accumulator, lo*hi + hi*lo -> CORR accumulator
+//   warps 4-11 drain: every `chunk` stages the MAIN accumulator (double buffered in TMEM) is read with tcgen05.ld and
+//            added to fp32 registers with round-to-nearest; epilogue adds CORR, bias, residual, ReLU; 128-bit stores.
+//
+// Why the chunked accumulation: the tensor core adds into its fp32 accumulator with truncation, a systematic
+// -0.5 ulp per MMA.  Over K = 2304 ... 18432 that bias reaches 1e-4 relative and broke the 1e-3 logit parity
+// (measured: 7e-4 abs on a 2048->256 3x3 conv, 1.6e-2 on the final logits).  Short TMEM chains (K = 128) summed
+// in registers, and the 2^-11-scaled correction terms kept in their own accumulator, bring the result back to
+// fp32-FMA quality.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace aoc {
+using namespace umma;
+
+constexpr int C2_BM = 128;
+constexpr int C2_KC = 16;                               // input channels per stage (2 k-steps of 8)
+constexpr int C2_NR = 8;                                // raw ring depth
+constexpr int C2_NO = 4;                                // operand ring depth
+constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_KC * 4;    // 8192
+constexpr uint32_t C2_A_BYTES = 2 * C2_RAW_BYTES;       // hi + lo
+constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
+constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
+constexpr int C2_MAX_AFFINE_C = 1024;
+constexpr int C2_THREADS = 512;
+
+struct Conv2P {
+    const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
+    int N, H, W, Cin, Ho, Wo, Cout, ldy, ldres, kw, stride, pad, dil, relu, in_relu;
+    int tw_log2, th, tiles_x, tiles_y;
+    int ncc, nIt, chunk;
+    int vec_out;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int TN>
+struct C2Cfg {
+    static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
+    static constexpr uint32_t OP_BYTES = C2_A_BYTES + B_BYTES;
+    static constexpr uint32_t RAW_OFF = 0;
+    static constexpr uint32_t OP_OFF = C2_NR * C2_RAW_BYTES;
+    static constexpr uint32_t TAB_OFF = OP_OFF + C2_NO * OP_BYTES;
+    static constexpr uint32_t BAR_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;
+    static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
+    static constexpr uint32_t TMEM_COLS = TN <= 64 ? 256 : 512;
+};
+
+template <int TN>
+__global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
+    using Cfg = C2Cfg<TN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* tab_a = reinterpret_cast<float*>(smem + Cfg::TAB_OFF);
+    float* tab_b = tab_a + C2_MAX_AFFINE_C;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    const uint32_t bar0 = smem_u32(bars);
+    auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto RAW_EMPTY = [&](int s) { return bar0 + 8u * (C2_NR + s); };
+    auto OP_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + s); };
+    auto OP_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + C2_NO + s); };
+    auto MAIN_FULL = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + b); };
+    auto MAIN_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 + b); };
+    const uint32_t raw0 = smem_u32(smem + Cfg::RAW_OFF);
+    const uint32_t op0 = smem_u32(smem + Cfg::OP_OFF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- tile decode: blockIdx.x -> (n, tile row, tile col), blockIdx.y -> output-channel tile
+    const int tpi = p.tiles_x * p.tiles_y;
+    const int n = blockIdx.x / tpi;
+    const int trem = blockIdx.x - n * tpi;
+    const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+    const int tw_mask = (1 << p.tw_log2) - 1;
+    const int ho0 = tyi * p.th, wo0 = txi << p.tw_log2;
+    const int n0 = blockIdx.y * TN;
+    const bool affine = p.in_a != nullptr || p.in_b != nullptr || p.in_relu;
+
+    if (warp == 15 && lane == 0) {
+        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
+        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 5); mbar_init(OP_EMPTY(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); }
+        fence_barrier_init();
+    }
+    if (warp == 14) {
+        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (affine) {
+        const int cpad = p.ncc * C2_KC;
+        for (int c = threadIdx.x; c < cpad; c += C2_THREADS) {
+            const bool ok = c < p.Cin;
+            tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)n * p.Cin + c) : 1.f) : 0.f;
+            tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)n * p.Cin + c) : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nIt = p.nIt;
+
+    if (warp < 4) {
+        // ===== transform warps: raw fp32 patch -> (affine, relu, mask) -> hi/lo operand blocks =====
+        const int t = threadIdx.x;
+        const int j = (t >> 3) & 3;                       // 16-byte channel granule of the stage (4 floats)
+        const int pbase = (t & 7) + 8 * (t >> 5);         // pixels pbase + 32 q
+        int hb[4], wb[4];
+        uint32_t src_off[4], dst_off[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int pp = pbase + 32 * q;
+            const int ty = pp >> p.tw_log2, tx = pp & tw_mask;
+            hb[q] = (ho0 + ty) * p.stride - p.pad;
+            wb[q] = (wo0 + tx) * p.stride - p.pad;
+            src_off[q] = (uint32_t)(pp * 64 + ((j ^ ((pp >> 1) & 3)) << 4));        // TMA SWIZZLE_64B
+            dst_off[q] = (uint32_t)((j >> 1) * (2 * C2_RAW_BYTES / 2) + (pp >> 3) * 256 + (j & 1) * 128 + (pp & 7) * 16);
+        }
+        const bool need_mask = p.in_b != nullptr;
+        int sr = 0, so = 0;
+        uint32_t pr = 0, po = 0;
+        int tap = 0, cc = 0;
+        for (int it = 0; it < nIt; ++it) {
+            mbar_wait(RAW_FULL(sr), pr);
+            mbar_wait(OP_EMPTY(so), po ^ 1u);
+            const uint32_t rawb = raw0 + sr * C2_RAW_BYTES;
+            const uint32_t opb = op0 + so * Cfg::OP_BYTES;
+            float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            int dh = 0, dw = 0;
+            if (affine) {
+                a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
+                b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
+                const int r = tap / p.kw, s = tap - r * p.kw;
+                dh = r * p.dil; dw = s * p.dil;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rawb + src_off[q]));
+                if (affine) {
+                    v.x = fmaf(v.x, a4.x, b4.x); v.y = fmaf(v.y, a4.y, b4.y);
+                    v.z = fmaf(v.z, a4.z, b4.z); v.w = fmaf(v.w, a4.w, b4.w);
+                    if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (need_mask) {
+                        const bool ok = (unsigned)(hb[q] + dh) < (unsigned)p.H && (unsigned)(wb[q] + dw) < (unsigned)p.W;
+                        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                float h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
+                const uint32_t d = opb + dst_off[q];
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d + C2_RAW_BYTES / 2), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(OP_FULL(so));
+                mbar_arrive(RAW_EMPTY(sr));
+            }
+            if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+            if (++so == C2_NO) { so = 0; po ^= 1u; }
+            if (++cc == p.ncc) { cc = 0; ++tap; }
+        }
+    } else if (warp < 12) {
+        // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
+        constexpr int NC = TN / 2;
+        const int dwp = warp - 4;
+        const int q = dwp & 3, half = dwp >> 2;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
+        float acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+        const int nchunks = (nIt + p.chunk - 1) / p.chunk;
+        int b = 0;
+        uint32_t ph[2] = {0u, 0u};
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait(MAIN_FULL(b), ph[b]);
+            ph[b] ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+                float v[32];
+                tmem_ld32(tlane + (uint32_t)(b * TN + c0), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
+            b ^= 1;
+        }
+        // all MMAs (including CORR) are complete once the last MAIN_FULL has fired
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 32) {
+            float v[32];
+            tmem_ld32(tlane + (uint32_t)(2 * TN + c0), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
+        }
+        const int m = q * 32 + lane;
+        const int ty = m >> p.tw_log2, tx = m & tw_mask;
+        const int ho = ho0 + ty, wo = wo0 + tx;
+        if (ho < p.Ho && wo < p.Wo) {
+            const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;
+            const int cbase = n0 + half * NC;
+            float* dst = p.y + pix * p.ldy + cbase;
+            const float* rsd = p.res ? p.res + pix * p.ldres + cbase : nullptr;
+#pragma unroll
+            for (int c4 = 0; c4 < NC / 4; ++c4) {
+                const int co = cbase + c4 * 4;
+                if (co < p.Cout) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        o[e] = acc[c4 * 4 + e];
+                        if (co + e < p.Cout) {
+                            if (p.bias) o[e] += __ldg(p.bias + co + e);
+                            if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
+                            if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                        }
+                    }
+                    if (p.vec_out && co + 3 < p.Cout) {
+                        *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (co + e < p.Cout) dst[c4 * 4 + e] = o[e];
+                    }
+                }
+            }
+        }
+    } else if (warp == 12) {
+        if (lane == 0) {
+            // ===== activation TMA producer =====
+            int sr = 0;
+            uint32_t pr = 0;
+            int tap = 0, cc = 0;
+            const int wbase = wo0 * p.stride - p.pad, hbase = ho0 * p.stride - p.pad;
+            for (int it = 0; it < nIt; ++it) {
+                mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
+                mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
+                const int r = tap / p.kw, s = tap - r * p.kw;
+                tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, cc * C2_KC, wbase + s * p.dil, hbase + r * p.dil, n,
+                            RAW_FULL(sr));
+                if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                if (++cc == p.ncc) { cc = 0; ++tap; }
+            }
+        }
+    } else if (warp == 13) {
+        if (lane == 0) {
+            // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
+            int so = 0;
+            uint32_t po = 0;
+            const int rb = n0 / C2_WRB;
+            const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
+            for (int it = 0; it < nIt; ++it) {
+                mbar_wait(OP_EMPTY(so), po ^ 1u);
+                mbar_arrive_expect_tx(OP_FULL(so), Cfg::B_BYTES);
+                const uint32_t sb = op0 + so * Cfg::OP_BYTES + C2_A_BYTES;
+                const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
+                if (TN == C2_WRB) {
+                    bulk_g2s(sb, src, C2_WCHUNK, OP_FULL(so));
+                } else {
+                    const uint32_t sub = (uint32_t)(n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk)
+                        bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, OP_FULL(so));
+                }
+                if (++so == C2_NO) { so = 0; po ^= 1u; }
+            }
+        }
+    } else if (warp == 14) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = idesc_tf32(C2_BM, TN);
+            const uint32_t d_corr = tmem_base + 2 * TN;
+            int so = 0, b = 0, in_chunk = 0;
+            uint32_t po = 0, pe[2] = {0u, 0u};
+            for (int it = 0; it < nIt; ++it) {
+                mbar_wait(OP_FULL(so), po);
+                if (in_chunk == 0) {
+                    mbar_wait(MAIN_EMPTY(b), pe[b] ^ 1u);
+                    pe[b] ^= 1u;
+                }
+                tc_fence_after();
+                const uint32_t sa = op0 + so * Cfg::OP_BYTES;
+                const uint32_t sb = sa + C2_A_BYTES;
+                const uint32_t d_main = tmem_base + (uint32_t)(b * TN);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t a_hi = sa + ks * C2_RAW_BYTES, a_lo = a_hi + C2_RAW_BYTES / 2;
+                    const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
+                    const uint64_t dah = smem_desc(a_hi, LBO_BYTES, SBO_BYTES), dal = smem_desc(a_lo, LBO_BYTES, SBO_BYTES);
+                    const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
+                    mma_tf32(d_main, dah, dbh, idesc, (in_chunk > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(d_corr, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(d_corr, dah, dbl, idesc, 1u);
+                }
+                mma_commit(OP_EMPTY(so));
+                if (++in_chunk == p.chunk || it == nIt - 1) {
+                    mma_commit(MAIN_FULL(b));
+                    b ^= 1;
+                    in_chunk = 0;
+                }
+                if (++so == C2_NO) { so = 0; po ^= 1u; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 14) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// w [Cout][taps][Cin] fp32 -> weight image: [row block of 128][stage it = (tap, cc)][ks][hi|lo][128 rows x 8 floats]
+__global__ void conv2_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ncc,
+                                          int rows_padded, uint8_t* __restrict__ out) {
+    const int nIt = taps * ncc;
+    const long long total = (long long)rows_padded * nIt * 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % rows_padded);
+        const long long rest = i / rows_padded;
+        const int g = (int)(rest & 3);                  // 4-float granule inside the 16-channel stage
+        const int it = (int)(rest >> 2);
+        const int tap = it / ncc, cc = it - tap * ncc;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int ci = cc * C2_KC + g * 4 + e;
+            const float v = (r < Cout && ci < Cin) ? __ldg(w + ((size_t)r * taps + tap) * Cin + ci) : 0.f;
+            split_tf32(v, hi[e], lo[e]);
+        }
+        const int rb = r / C2_WRB, rr = r - rb * C2_WRB;
+        const int ks = g >> 1, half = g & 1;
+        const size_t base = ((size_t)rb * nIt + it) * C2_WCHUNK + (size_t)ks * 8192 + elem_offset(rr, half * 4);
+        *reinterpret_cast<float4*>(out + base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(out + base + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+template <int TN>
+static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(conv2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
+        attr = true;
+    }
+    dim3 grid(tiles, cdiv(p.Cout, TN));
+    conv2_kernel<TN><<<grid, C2_THREADS, C2Cfg<TN>::SMEM, stream>>>(map, p);
+    return launch_status("aoc_conv2d_nhwc_tc");
+}
+
+}  // namespace aoc
+
+using namespace aoc;
+
+extern "C" size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw) {
+    const size_t ncc = (size_t)cdiv(Cin, C2_KC);
+    return (size_t)cdiv(Cout, C2_WRB) * kh * kw * ncc * C2_WCHUNK;
+}
+
+extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
+                                            cudaStream_t stream) {
+    AOC_CHECK_ARG(w && w_packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "bad args");
+    const int ncc = cdiv(Cin, C2_KC);
+    const int rows_padded = cdiv(Cout, C2_WRB) * C2_WRB;
+    const long long total = (long long)rows_padded * kh * kw * ncc * 4;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    conv2_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
+    return launch_status("aoc_conv_pack_weights_tf32x3");
+}
+
+extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
+                                  const float* in_a, const float* in_b, int in_relu, float* y, int N, int H, int W,
+                                  int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad,
+                                  int dil, int relu, int chunk_stages, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && w_packed && y, "null pointer");
+    AOC_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && dil > 0, "bad dims");
+    AOC_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
+    AOC_CHECK_ARG(ldx % 4 == 0 && (((uintptr_t)x) & 15) == 0, "ldx must be a multiple of 4 and x 16-byte aligned");
+    const bool affine = in_a || in_b || in_relu;
+    AOC_CHECK_ARG(!affine || Cin <= C2_MAX_AFFINE_C, "fused input affine supports Cin <= 1024");
+    EncodeTiledFn encode = get_encode();
+    if (!encode) {
+        set_error("aoc_conv2d_nhwc_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver)");
+        return AOC_ELAUNCH;
+    }
+    int Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1;
+    int Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+    AOC_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
+    Conv2P p;
+    p.w = (const uint8_t*)w_packed; p.bias = bias; p.res = residual; p.in_a = in_a; p.in_b = in_b; p.y = y;
+    p.N = N; p.Cin = Cin; p.Cout = Cout; p.ldy = ldy; p.ldres = ldres; p.kw = kw; p.stride = stride; p.pad = pad;
+    p.dil = dil; p.relu = relu; p.in_relu = in_relu;
+    p.ncc = cdiv(Cin, C2_KC);
+    p.nIt = kh * kw * p.ncc;
+    p.chunk = chunk_stages > 0 ? chunk_stages : 8;
+    p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
+    // pixel-patch geometry: 1x1/s1/p0 convolutions see each image as one row of H*W pixels
+    int gW = W, gH = H;
+    if (kh == 1 && kw == 1 && stride == 1 && pad == 0) { gW = H * W; gH = 1; Wo = gW; Ho = 1; }
+    int best_l2 = 7;
+    long long best_tiles = -1;
+    for (int l2 = 7; l2 >= 3; --l2) {
+        int tw = 1 << l2, th = C2_BM >> l2;
+        long long t = (long long)cdiv(Wo, tw) * cdiv(Ho, th);
+        if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_l2 = l2; }
+    }
+    p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
+    p.tw_log2 = best_l2;
+    p.th = C2_BM >> best_l2;
+    const int tw = 1 << best_l2;
+    p.tiles_x = cdiv(Wo, tw);
+    p.tiles_y = cdiv(Ho, p.th);
+    CUtensorMap map;
+    cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)gW * ldx * 4, (cuuint64_t)gH * gW * ldx * 4};
+    cuuint32_t box[4] = {(cuuint32_t)C2_KC, (cuuint32_t)(tw * stride), (cuuint32_t)(p.th * stride), 1u};
+    cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
+    CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("aoc_conv2d_nhwc_tc: cuTensorMapEncodeTiled failed (%d) dims %d x %d x %d x %d ld %d box %d x %d", (int)cr, Cin,
+                  gW, gH, N, ldx, tw * stride, p.th * stride);
+        return AOC_EINVAL;
+    }
+    const int tiles = N * p.tiles_x * p.tiles_y;
+    // narrow N tile when the layer is too small to fill the chip with 128-wide tiles
+    const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148;
+    if (narrow) return launch_conv2<64>(map, p, tiles, stream);
+    return launch_conv2<128>(map, p, tiles, stream);
+}

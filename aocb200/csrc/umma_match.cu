@@ -27,8 +27,13 @@ constexpr uint32_t SMEM_MATCH = A_BYTES + NST * B_STAGE + 256;
 
 // x [R][ld] fp32 (first K_valid columns used, zero beyond; rows >= R zero) -> tc image with row blocks of RB rows,
 // K = ksteps*8 columns.  One thread per (row, float4 granule).
+//
+// center (optional, [>= K_valid]): the image holds x - center (the matching distances are invariant to a common
+// translation of queries and bank rows; centred operands keep the truncating TMEM accumulation near zero, see
+// aoc_global_match_tc).  valid_r2 (optional, [R]): rows whose entry is +inf are padding and stay zero.
 __global__ void pack_tc_image_kernel(const float* __restrict__ x, int R, int K_valid, int ld, int RB, int ksteps,
-                                     long long rows_padded, uint8_t* __restrict__ out) {
+                                     long long rows_padded, uint8_t* __restrict__ out,
+                                     const float* __restrict__ center, const float* __restrict__ valid_r2) {
     long long total = rows_padded * ksteps * 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -36,11 +41,11 @@ __global__ void pack_tc_image_kernel(const float* __restrict__ x, int R, int K_v
         int g = (int)(i / rows_padded);           // granule index: k = 4*g
         int ks = g >> 1, half = g & 1;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (r < R) {
+        if (r < R && !(valid_r2 && isinf(__ldg(valid_r2 + r)))) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 int k = g * 4 + e;
-                if (k < K_valid) v[e] = __ldg(x + (size_t)r * ld + k);
+                if (k < K_valid) v[e] = __ldg(x + (size_t)r * ld + k) - (center ? __ldg(center + k) : 0.f);
             }
         }
         float hi[4], lo[4];
@@ -207,6 +212,51 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
     }
 }
 
+// column means of x [rows][100]: part[b][100] partial sums over a fixed row slab (deterministic), then mu[k]
+__global__ void __launch_bounds__(256) col_sum_partial_kernel(const float* __restrict__ x, int rows, int slab,
+                                                               float* __restrict__ part) {
+    __shared__ float sm[8][104];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int r0 = blockIdx.x * slab, r1 = min(rows, r0 + slab);
+    if (lane < 25)
+        for (int r = r0 + warp; r < r1; r += 8) {
+            float4 v = ldg4(x + (size_t)r * 100 + lane * 4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    if (lane < 25) *reinterpret_cast<float4*>(&sm[warp][lane * 4]) = a;
+    __syncthreads();
+    if (threadIdx.x < 100) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        part[(size_t)blockIdx.x * 100 + threadIdx.x] = t;
+    }
+}
+__global__ void col_mean_final_kernel(const float* __restrict__ part, int nb, int rows, float* __restrict__ mu) {
+    int k = threadIdx.x;
+    if (k >= 104) return;
+    double t = 0.0;
+    if (k < 100)
+        for (int b = 0; b < nb; ++b) t += (double)part[(size_t)b * 100 + k];
+    mu[k] = (float)(t / (double)rows);
+}
+// out[row] = |x[row] - center|^2 (warp per row); rows flagged +inf in valid_r2 (padding) keep +inf
+__global__ void centered_sqnorm_kernel(const float* __restrict__ x, int rows, const float* __restrict__ center,
+                                       const float* __restrict__ valid_r2, float* __restrict__ out) {
+    int lane = threadIdx.x & 31;
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    float s = 0.f;
+    if (lane < 25) {
+        float4 v = ldg4(x + (size_t)row * 100 + lane * 4);
+        float4 c = ldg4(center + lane * 4);
+        v.x -= c.x; v.y -= c.y; v.z -= c.z; v.w -= c.w;
+        s = v.x * v.x; s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = (valid_r2 && isinf(valid_r2[row])) ? INFINITY : s;
+}
+
 __global__ void fill_f32_kernel(float* p, float v, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         p[i] = v;
@@ -249,34 +299,64 @@ extern "C" int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int 
     long long total = rows_padded * ks * 2;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, K, ld, RB, ks, rows_padded, (uint8_t*)out);
+    pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, K, ld, RB, ks, rows_padded, (uint8_t*)out, nullptr,
+                                                     nullptr);
     return launch_status("aoc_pack_tc_image_f32");
 }
 
-extern "C" size_t aoc_global_match_tc_workspace_bytes(int HW) {
-    // query image (RB=128) + |q|^2 + mins[16 splits][HW][MAXO]
-    size_t img = aoc_tc_image_bytes(HW, TC_K, QB);
-    return img + (size_t)(HW + QB) * sizeof(float) + (size_t)16 * HW * MAXO_ * sizeof(float) + 1024;
+static int pack_centered(const float* x, long long rows, int RB, const float* center, const float* valid_r2, void* out,
+                         cudaStream_t stream) {
+    int ks = TC_KS;
+    long long rows_padded = (rows + RB - 1) / RB * RB;
+    long long total = rows_padded * ks * 2;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, 100, 100, RB, ks, rows_padded, (uint8_t*)out, center,
+                                                     valid_r2);
+    return launch_status("aoc_global_match_tc(pack)");
 }
 
-// q [HW][100]; S_tc = tc image (RB=256) of the sorted bank rows (aoc_pack_tc_image_f32 of S), r2 = |row|^2 (+inf pad);
-// meta (device) as written by aoc_bank_index_build with align = 256; rows_padded = meta[2*MAXO+1] (host copy).
-extern "C" int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev,
+constexpr int MU_SLAB = 512;
+
+extern "C" size_t aoc_global_match_tc_workspace_bytes(int HW, int rows_padded) {
+    // query image (RB=128) + bank image (RB=256) + |q-mu|^2 + |r-mu|^2 + mu + column-sum partials + mins[16][HW][MAXO]
+    size_t img = aoc_tc_image_bytes(HW, TC_K, QB) + aoc_tc_image_bytes(rows_padded > 0 ? rows_padded : 1, TC_K, RBK);
+    size_t vec = (size_t)((HW + QB + 3) & ~3) + (size_t)(rows_padded + RBK) + 128 + (size_t)(cdiv(HW, MU_SLAB) + 1) * 100;
+    return img + vec * sizeof(float) + (size_t)16 * HW * MAXO_ * sizeof(float) + 4096;
+}
+
+// q [HW][100]; S [rows_padded][100] = object-sorted bank rows (aoc_bank_gather_f32, align = 256) with r2 = |row|^2
+// (+inf on padding rows); meta (device) as written by aoc_bank_index_build; rows_padded = meta[2*MAXO+1] (host copy).
+// Queries and bank rows are translated by mu = column mean of q before the contraction: |q - r|^2 is unchanged, but
+// the dot products q'.r' hover around zero instead of growing monotonically (embeddings are post-ReLU, all >= 0), which
+// removes most of the truncation bias of the TMEM accumulation and most of the cancellation in |q|^2+|r|^2-2q.r.
+extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const float* r2, const int* meta_dev,
                                    int rows_padded, const float* bias, int O, void* workspace, size_t ws_bytes,
                                    float* out, cudaStream_t stream) {
-    AOC_CHECK_ARG(q && S_tc && r2 && meta_dev && bias && workspace && out, "null pointer");
+    AOC_CHECK_ARG(q && S && r2 && meta_dev && bias && workspace && out, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO_ && HW > 0 && rows_padded % RBK == 0, "bad dims");
-    AOC_CHECK_ARG(ws_bytes >= aoc_global_match_tc_workspace_bytes(HW), "workspace too small");
+    AOC_CHECK_ARG(ws_bytes >= aoc_global_match_tc_workspace_bytes(HW, rows_padded), "workspace too small");
     uint8_t* ws = (uint8_t*)workspace;
-    size_t img = aoc_tc_image_bytes(HW, TC_K, QB);
+    size_t imgq = aoc_tc_image_bytes(HW, TC_K, QB), imgs = aoc_tc_image_bytes(rows_padded > 0 ? rows_padded : 1, TC_K, RBK);
     uint8_t* Qimg = ws;
-    float* q2 = (float*)(ws + img);
-    float* mins = q2 + (HW + QB);
+    uint8_t* Simg = ws + imgq;
+    float* q2 = (float*)(ws + imgq + imgs);
+    float* r2c = q2 + ((HW + QB + 3) & ~3);            // keeps r2c / mu 16-byte aligned (float4 loads)
+    float* mu = r2c + (rows_padded + RBK);
+    float* part = mu + 128;
+    float* mins = part + (size_t)(cdiv(HW, MU_SLAB) + 1) * 100;
     int nqt = cdiv(HW, QB), nrb = rows_padded / RBK;
-    int rc = aoc_pack_tc_image_f32(q, HW, 100, 100, QB, TC_K, Qimg, stream);
+    int nb = cdiv(HW, MU_SLAB);
+    col_sum_partial_kernel<<<nb, 256, 0, stream>>>(q, HW, MU_SLAB, part);
+    col_mean_final_kernel<<<1, 128, 0, stream>>>(part, nb, HW, mu);
+    int rc = pack_centered(q, HW, QB, mu, nullptr, Qimg, stream);
     if (rc) return rc;
-    rc = aoc_row_sqnorm_f32(q, HW, q2, stream);
-    if (rc) return rc;
+    centered_sqnorm_kernel<<<cdiv((long long)HW * 32, 256), 256, 0, stream>>>(q, HW, mu, nullptr, q2);
+    if (nrb > 0) {
+        rc = pack_centered(S, rows_padded, RBK, mu, r2, Simg, stream);
+        if (rc) return rc;
+        centered_sqnorm_kernel<<<cdiv((long long)rows_padded * 32, 256), 256, 0, stream>>>(S, rows_padded, mu, r2, r2c);
+    }
     int nsplit = nrb > 0 ? pick_splits(nqt, nrb) : 1;
     long long n = (long long)HW * O;
     fill_f32_kernel<<<cdiv(n * nsplit, 1024), 256, 0, stream>>>(mins, INFINITY, n * nsplit);
@@ -286,8 +366,8 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const void* S_tc, con
             g_attr0 = true;
         }
         dim3 grid(nqt, nsplit);
-        match_tc_kernel<0><<<grid, 256, SMEM_MATCH, stream>>>(Qimg, (const uint8_t*)S_tc, q2, r2, meta_dev, O, HW, nrb,
-                                                             nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
+        match_tc_kernel<0><<<grid, 256, SMEM_MATCH, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb, nsplit, mins,
+                                                             nullptr, 0, LBO_BYTES, SBO_BYTES);
         if (nsplit > 1) min_over_splits_kernel<<<cdiv(n, 256), 256, 0, stream>>>(mins, n, nsplit);
     }
     rc = aoc_global_match_finalize_f32(mins, meta_dev, bias, HW, O, out, stream);

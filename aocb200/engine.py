@@ -143,9 +143,10 @@ class Engine:
         self.keep_debug = False
         # tensor-core (tcgen05, 3xTF32) kernels vs the fp32 SIMT kernels; both are CUDA, same results to ~1e-6 relative
         tc = os.environ.get("AOCB200_TC", "1") != "0"
-        self.tc_conv = tc
-        self.tc_match = tc
+        self.tc_conv = tc and os.environ.get("AOCB200_TC_CONV", "1") != "0"
+        self.tc_match = tc and os.environ.get("AOCB200_TC_MATCH", "1") != "0"
         self._wpacked = {}
+        self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self._ws = {}
 
@@ -169,7 +170,9 @@ class Engine:
         return b
 
     # ------------------------------------------------------------------ layer helpers
-    def conv(self, x, name, stride=1, pad=0, dil=1, relu=False, res=None, in_scale=None, out=None):
+    def conv(self, x, name, stride=1, pad=0, dil=1, relu=False, res=None, in_scale=None, out=None, in_shift=None,
+             in_relu=False):
+        """y = conv(relu?(x * in_scale[n,c] + in_shift[n,c])) + bias (+ res) (ReLU)"""
         w, b, (Cout, kh, kw, Cin) = self.w.conv[name]
         assert Cin == x.C, (name, Cin, x.C)
         Ho = (x.H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
@@ -177,18 +180,19 @@ class Engine:
         if out is None:
             out = self.new(x.N, Ho, Wo, Cout)
         assert out.C == Cout and out.H == Ho and out.W == Wo and out.N == x.N
-        if self.tc_conv and Cin % 4 == 0 and x.ld % 4 == 0:
+        if self.tc_conv:
             wp = self._wpacked.get(name)
             if wp is None or wp[0] is not w:
-                K = kh * kw * Cin
-                buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, K), dtype=torch.uint8, device=self.dev)
-                self.L.conv_pack_weights_tf32x3(w.data_ptr(), Cout, K, buf.data_ptr(), self.stream)
+                buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, Cin, kh, kw), dtype=torch.uint8, device=self.dev)
+                self.L.conv_pack_weights_tf32x3(w.data_ptr(), Cout, Cin, kh, kw, buf.data_ptr(), self.stream)
                 wp = (w, buf)
                 self._wpacked[name] = wp
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
-                                  out.ptr, x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw,
-                                  stride, pad, dil, 1 if relu else 0, self.stream)
+                                  _p(in_shift), 1 if in_relu else 0, out.ptr, x.N, x.H, x.W, Cin, x.ld, Cout, out.ld,
+                                  0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
+                                  self.conv_chunk, self.stream)
             return out
+        assert in_shift is None and not in_relu, "the fp32 SIMT convolution only fuses an input scale"
         self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
                                x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw, stride,
                                pad, dil, 1 if relu else 0, self.stream)
@@ -394,11 +398,8 @@ class Engine:
         # --- pixel-level global matching (matching.py:2384)
         g = self.empty(hw * O)
         if self.tc_match and rows > 0:
-            nimg = L.tc_image_bytes(rows, 104, 256)
-            S_tc = self.ws("bank_tc", nimg)
-            L.pack_tc_image_f32(S.data_ptr(), rows, EMB, EMB, 256, 104, S_tc.data_ptr(), st)
-            nws2 = L.global_match_tc_workspace_bytes(hw)
-            L.global_match_tc(q.ptr, hw, S_tc.data_ptr(), r2.data_ptr(), meta.data_ptr(), rows, bias.data_ptr(), O,
+            nws2 = L.global_match_tc_workspace_bytes(hw, rows)
+            L.global_match_tc(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), rows, bias.data_ptr(), O,
                               self.ws("gm_tc", nws2).data_ptr(), nws2, g.data_ptr(), st)
         else:
             mins = self.empty(hw * O)

@@ -177,7 +177,7 @@ def kernel_profile(model, frames, first, device, n_frames):
     if conv:
         fl, ms = 0.0, 0.0
         for e0, e1, a in conv:
-            N, H, W, Cin, Cout, kh, kw, stride, pad, dil = a[6], a[7], a[8], a[9], a[11], a[14], a[15], a[16], a[17], a[18]
+            N, H, W, Cin, Cout, kh, kw, stride, pad, dil = a[8], a[9], a[10], a[11], a[13], a[16], a[17], a[18], a[19], a[20]
             Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
             Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
             fl += 2.0 * N * Ho * Wo * Cout * kh * kw * Cin

@@ -48,7 +48,7 @@ const char* aoc_last_error_string(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
 int aoc_check_device(int dev);
 
-/* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv.cu) */
+/* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */
 /* nn.Conv2d (+ folded FrozenBatchNorm2d bias, + residual, + ReLU): resnet.py:23-42,108-123; deeplab/aspp.py:62-74;
  * deeplab/decoder.py:32-41; layers/gct.py:68-91; layers/aspp.py:57-70; decoding_module.py:162-190,228-240.
  * x [N][H][W][ldx>=Cin], w [Cout][kh][kw][Cin], y [N][Ho][Wo][ldy>=Cout]; in_scale (optional) [N][Cin] multiplies the
@@ -56,13 +56,20 @@ int aoc_check_device(int dev);
 int aoc_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, const float* residual,
                         const float* in_scale, float* y, int N, int H, int W, int Cin, int ldx, int Cout, int ldy,
                         int ldres, int kh, int kw, int stride, int pad, int dil, int relu, cudaStream_t stream);
-/* Same contract on the tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM).  w_packed comes from
- * aoc_conv_pack_weights_tf32x3 (size aoc_conv_packed_weight_bytes).  Requires Cin % 4 == 0. */
-size_t aoc_conv_packed_weight_bytes(int Cout, int K);
-int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int K, void* w_packed, cudaStream_t stream);
+/* Same contract on the tcgen05 tensor cores (csrc/umma_conv2.cu): 3xTF32 split operands, fp32 accumulate in TMEM in
+ * chains of `chunk_stages` x 16 input channels that are summed in fp32 registers (round to nearest), so the result
+ * has fp32-FMA quality for any K.  The activation patch is fetched by TMA (zero fill = padding) and the
+ * per-(sample, channel) affine that precedes the convolution in the reference is fused into the operand path:
+ *     x_eff = relu?(x * in_a[n,c] + in_b[n,c])      (GroupNorm apply + ReLU, GCT gate, IA gate; each optional)
+ * w_packed comes from aoc_conv_pack_weights_tf32x3 (size aoc_conv_packed_weight_bytes).  Requires ldx % 4 == 0,
+ * stride in {1, 2}; Cin <= 1024 when an input affine is given.  chunk_stages <= 0 selects the default (8). */
+size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
+int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
+                                 cudaStream_t stream);
 int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
-                       const float* in_scale, float* y, int N, int H, int W, int Cin, int ldx, int Cout, int ldy,
-                       int ldres, int kh, int kw, int stride, int pad, int dil, int relu, cudaStream_t stream);
+                       const float* in_a, const float* in_b, int in_relu, float* y, int N, int H, int W, int Cin,
+                       int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad, int dil, int relu,
+                       int chunk_stages, cudaStream_t stream);
 /* depthwise 3x3 pad 1 + bias (aocnet.py:19 seperate_conv); w [C][3][3] */
 int aoc_dwconv3x3_nhwc_f32(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C,
                            cudaStream_t stream);
@@ -133,10 +140,12 @@ int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int ld, int RB,
 /* global_matching_for_eval (matching.py:2384-2510): out [HW][O] */
 int aoc_global_match_simt_f32(const float* q, int HW, const float* S, const float* r2, const int* meta,
                               const float* bias, int O, float* mins_ws, float* out, cudaStream_t stream);
-/* Same result on the tcgen05 tensor cores (3xTF32, TMEM accumulators, TMA-fed): S_tc = tc image (RB = 256,
- * K_img = 104) of the sorted bank built with align = 256; rows_padded = meta[2*AOC_MAX_OBJECTS+1]. */
-size_t aoc_global_match_tc_workspace_bytes(int HW);
-int aoc_global_match_tc(const float* q, int HW, const void* S_tc, const float* r2, const int* meta_dev, int rows_padded,
+/* Same result on the tcgen05 tensor cores (3xTF32, TMEM accumulators, TMA-fed).  S / r2 = sorted bank rows and their
+ * squared norms (+inf on padding rows) from aoc_bank_gather_f32 built with align = 256; rows_padded =
+ * meta[2*AOC_MAX_OBJECTS+1].  Both operands are translated by the column mean of q and packed into tc images inside
+ * the workspace (|q-r|^2 is translation invariant; centred operands keep the TMEM accumulation unbiased). */
+size_t aoc_global_match_tc_workspace_bytes(int HW, int rows_padded);
+int aoc_global_match_tc(const float* q, int HW, const float* S, const float* r2, const int* meta_dev, int rows_padded,
                         const float* bias, int O, void* workspace, size_t ws_bytes, float* out, cudaStream_t stream);
 int aoc_global_match_finalize_f32(const float* mins, const int* meta, const float* bias, int HW, int O, float* out,
                                   cudaStream_t stream);

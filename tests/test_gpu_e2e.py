@@ -31,7 +31,9 @@ def test_extract_feature_vs_oracle(model, state_dict):
         emb_w, low_w = extract_feature(frames[:1], state_dict)
     emb, low = model.extract_feature(frames[:1].cuda())
     report("low-level feature", low, low_w, 2e-4)
-    report("embedding", emb, emb_w, 2e-4)
+    # two GroupNorms (divide by a per-group std) follow the backbone: the same ~4e-5 summation-order noise seen on
+    # `low` is amplified ~10x on the embedding (values up to 5.6 -> 7e-5 relative)
+    report("embedding", emb, emb_w, 1e-3)
 
 
 def test_decoder_vs_oracle(model, state_dict):
@@ -103,7 +105,10 @@ def test_sequence_vs_reference_fixture(model, path):
         assert d_ref <= 1e-3 + d_64 + n_ref, (t, d_ref)
         if mism.any():
             up = F.interpolate(truth, size=(g["H"], g["W"]), mode="bilinear", align_corners=True)[0]
-            top2 = torch.topk(up, 2, dim=0)[0]
+            # the eval loop zeroes the probabilities of ids never seen in a ground-truth frame
+            # (eval_manager_mm.py:252-261), so the contest is among the existing ids only
+            exist = sorted(int(v) for v in torch.unique(first).tolist())
+            top2 = torch.topk(up[exist], 2, dim=0)[0]
             margin = (top2[0] - top2[1])[mism]
             assert margin.max().item() <= 2.0 * (d_64 + n_ref), ("argmax differs away from a numerical tie", margin.max().item())
             assert mism.float().mean().item() < 1e-3
