@@ -1,6 +1,7 @@
 // Error reporting, version and device check of libaocb200.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -14,7 +15,15 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace aoc
 
-extern "C" int aoc_version(void) { return 100; }
+namespace aoc { extern int g_conv_ts; }
+
+extern "C" int aoc_version(void) { return 101; }
+
+extern "C" int aoc_set_option(const char* key, int value) {
+    if (key && !strcmp(key, "conv_ts")) { aoc::g_conv_ts = value ? 1 : 0; return AOC_OK; }
+    aoc::set_error("aoc_set_option: unknown option '%s'", key ? key : "(null)");
+    return AOC_EINVAL;
+}
 
 extern "C" const char* aoc_last_error_string(void) { return aoc::g_err; }
 

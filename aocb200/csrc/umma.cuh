@@ -32,12 +32,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // x = hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi): both exactly representable in TF32 (low 13 mantissa
 // bits zero), so the tensor core's operand conversion is a no-op and the residual errors (lo*lo' dropped, rounding of
 // lo) are zero-mean ~2^-22 relative per product instead of a truncation bias.
+__device__ __forceinline__ float rna_tf32(float x) {
+    // == cvt.rna.tf32.f32 for finite x (round the magnitude to 10 explicit mantissa bits, ties away from zero), but on
+    // the integer ALU at full rate instead of the quarter-rate conversion pipe
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-    lo = __uint_as_float(l);
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -99,6 +101,18 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 rows = TMEM lanes, one 32-bit column per k element) is read from
+// tensor memory, which leaves the shared-memory port to the B operand and the TMA writes
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -118,6 +132,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 registers per thread -> 32 consecutive columns of the thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1 = sm_100)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -55,21 +55,26 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int TN>
+// TS = true: the split activation operand lives in TENSOR memory (written with tcgen05.st, read by tcgen05.mma as the A
+// operand), so shared memory only carries the raw patch and the weights -- the SS variant (both operands in shared
+// memory) is bound by the 128 B/clk shared-memory port at about half the tensor rate.
+template <int TN, bool TS>
 struct C2Cfg {
     static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
-    static constexpr uint32_t OP_BYTES = C2_A_BYTES + B_BYTES;
+    static constexpr uint32_t A_SMEM = TS ? 0u : C2_A_BYTES;
+    static constexpr uint32_t OP_BYTES = A_SMEM + B_BYTES;
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = C2_NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + C2_NO * OP_BYTES;
     static constexpr uint32_t BAR_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
-    static constexpr uint32_t TMEM_COLS = TN <= 64 ? 256 : 512;
+    static constexpr uint32_t TMEM_COLS = TS ? 512 : (TN <= 64 ? 256 : 512);
+    static constexpr uint32_t A_TMEM_COL = 3 * TN;           // TS: ring of C2_NO stages x 32 columns
 };
 
-template <int TN>
+template <int TN, bool TS>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
-    using Cfg = C2Cfg<TN>;
+    using Cfg = C2Cfg<TN, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* tab_a = reinterpret_cast<float*>(smem + Cfg::TAB_OFF);
@@ -121,7 +126,76 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
     const int nIt = p.nIt;
 
-    if (warp < 4) {
+    if (warp < 4 && TS) {
+        // ===== transform warps (TS): thread <-> pixel row <-> TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
+        const int pp = threadIdx.x;
+        const int ty = pp >> p.tw_log2, tx = pp & tw_mask;
+        const int hb = (ho0 + ty) * p.stride - p.pad, wb = (wo0 + tx) * p.stride - p.pad;
+        const uint32_t src_row = (uint32_t)(pp * 64);
+        const uint32_t sw = (uint32_t)((pp >> 1) & 3);                       // TMA SWIZZLE_64B
+        const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + Cfg::A_TMEM_COL;
+        const bool need_mask = p.in_b != nullptr;
+        int sr = 0, so = 0;
+        uint32_t pr = 0, po = 0;
+        int tap = 0, cc = 0;
+        float v[16];
+        auto load_raw = [&]() {         // waits for raw stage sr and pulls this thread's 16 channels into registers
+            mbar_wait(RAW_FULL(sr), pr);
+            const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                             : "r"(rawb + ((j ^ sw) << 4)));
+        };
+        if (nIt > 0) load_raw();
+        for (int it = 0; it < nIt; ++it) {
+            if (affine) {
+                bool ok = true;
+                if (need_mask) {
+                    const int r = tap / p.kw, s = tap - r * p.kw;
+                    ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s * p.dil) < (unsigned)p.W;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
+                    v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
+                    v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
+                }
+                if (p.in_relu) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                if (!ok) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                }
+            }
+            // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
+            float o[32];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float h, l;
+                split_tf32(v[e], h, l);
+                o[(e >> 3) * 16 + (e & 7)] = h;
+                o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(RAW_EMPTY(sr));          // raw stage consumed (values are in registers)
+            if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+            if (it + 1 < nIt) load_raw();                       // next stage's loads fly while this one is stored
+            mbar_wait(OP_EMPTY(so), po ^ 1u);
+            tc_fence_after();
+            tmem_st32(a_lane + (uint32_t)(so * 32), o);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(OP_FULL(so));
+            if (++so == C2_NO) { so = 0; po ^= 1u; }
+            if (++cc == p.ncc) { cc = 0; ++tap; }
+        }
+    } else if (warp < 4) {
         // ===== transform warps: raw fp32 patch -> (affine, relu, mask) -> hi/lo operand blocks =====
         const int t = threadIdx.x;
         const int j = (t >> 3) & 3;                       // 16-byte channel granule of the stage (4 floats)
@@ -281,7 +355,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
             for (int it = 0; it < nIt; ++it) {
                 mbar_wait(OP_EMPTY(so), po ^ 1u);
                 mbar_arrive_expect_tx(OP_FULL(so), Cfg::B_BYTES);
-                const uint32_t sb = op0 + so * Cfg::OP_BYTES + C2_A_BYTES;
+                const uint32_t sb = op0 + so * Cfg::OP_BYTES + Cfg::A_SMEM;
                 const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
                 if (TN == C2_WRB) {
                     bulk_g2s(sb, src, C2_WCHUNK, OP_FULL(so));
@@ -309,17 +383,25 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 }
                 tc_fence_after();
                 const uint32_t sa = op0 + so * Cfg::OP_BYTES;
-                const uint32_t sb = sa + C2_A_BYTES;
+                const uint32_t sb = sa + Cfg::A_SMEM;
                 const uint32_t d_main = tmem_base + (uint32_t)(b * TN);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    const uint32_t a_hi = sa + ks * C2_RAW_BYTES, a_lo = a_hi + C2_RAW_BYTES / 2;
                     const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
-                    const uint64_t dah = smem_desc(a_hi, LBO_BYTES, SBO_BYTES), dal = smem_desc(a_lo, LBO_BYTES, SBO_BYTES);
                     const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
-                    mma_tf32(d_main, dah, dbh, idesc, (in_chunk > 0 || ks > 0) ? 1u : 0u);
-                    mma_tf32(d_corr, dal, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                    mma_tf32(d_corr, dah, dbl, idesc, 1u);
+                    const uint32_t acc_main = (in_chunk > 0 || ks > 0) ? 1u : 0u, acc_corr = (it > 0 || ks > 0) ? 1u : 0u;
+                    if (TS) {
+                        const uint32_t ta_hi = tmem_base + Cfg::A_TMEM_COL + (uint32_t)(so * 32 + ks * 16), ta_lo = ta_hi + 8;
+                        mma_tf32_ts(d_main, ta_hi, dbh, idesc, acc_main);
+                        mma_tf32_ts(d_corr, ta_lo, dbh, idesc, acc_corr);
+                        mma_tf32_ts(d_corr, ta_hi, dbl, idesc, 1u);
+                    } else {
+                        const uint32_t a_hi = sa + ks * C2_RAW_BYTES, a_lo = a_hi + C2_RAW_BYTES / 2;
+                        const uint64_t dah = smem_desc(a_hi, LBO_BYTES, SBO_BYTES), dal = smem_desc(a_lo, LBO_BYTES, SBO_BYTES);
+                        mma_tf32(d_main, dah, dbh, idesc, acc_main);
+                        mma_tf32(d_corr, dal, dbh, idesc, acc_corr);
+                        mma_tf32(d_corr, dah, dbl, idesc, 1u);
+                    }
                 }
                 mma_commit(OP_EMPTY(so));
                 if (++in_chunk == p.chunk || it == nIt - 1) {
@@ -384,17 +466,19 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int TN>
+template <int TN, bool TS>
 static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, TS>::SMEM);
         attr = true;
     }
     dim3 grid(tiles, cdiv(p.Cout, TN));
-    conv2_kernel<TN><<<grid, C2_THREADS, C2Cfg<TN>::SMEM, stream>>>(map, p);
+    conv2_kernel<TN, TS><<<grid, C2_THREADS, C2Cfg<TN, TS>::SMEM, stream>>>(map, p);
     return launch_status("aoc_conv2d_nhwc_tc");
 }
+
+int g_conv_ts = 1;      // aoc_set_option("conv_ts", 0/1)
 
 }  // namespace aoc
 
@@ -475,6 +559,6 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     const int tiles = N * p.tiles_x * p.tiles_y;
     // narrow N tile when the layer is too small to fill the chip with 128-wide tiles
     const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148;
-    if (narrow) return launch_conv2<64>(map, p, tiles, stream);
-    return launch_conv2<128>(map, p, tiles, stream);
+    if (g_conv_ts) return narrow ? launch_conv2<64, true>(map, p, tiles, stream) : launch_conv2<128, true>(map, p, tiles, stream);
+    return narrow ? launch_conv2<64, false>(map, p, tiles, stream) : launch_conv2<128, false>(map, p, tiles, stream);
 }

@@ -47,6 +47,9 @@ int aoc_version(void);
 const char* aoc_last_error_string(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
 int aoc_check_device(int dev);
+/* tuning / diagnostic switches.  "conv_ts" (default 1): the tensor-core convolution keeps its split activation operand
+ * in tensor memory (1) or in shared memory (0); both give identical results. */
+int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */
 /* nn.Conv2d (+ folded FrozenBatchNorm2d bias, + residual, + ReLU): resnet.py:23-42,108-123; deeplab/aspp.py:62-74;

@@ -39,11 +39,15 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.frames):
         st.step()
+    t_issue = time.perf_counter() - t0
     e1.record()
     torch.cuda.synchronize()
+    print("host issue time %.3f ms/frame (python + launches, GPU running behind)" % (1e3 * t_issue / args.frames))
     torch.cuda.profiler.stop()
     print("frames %d  %.3f ms/frame (%dx%d, K=%d)" % (args.frames, e0.elapsed_time(e1) / args.frames, H, W, args.K))
 
