@@ -29,6 +29,21 @@ __host__ __device__ inline uint32_t elem_offset(int r, int k) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// warp index as a value the compiler can prove warp-uniform (so role branches and everything derived from loop
+// counters inside them live in uniform registers -- the tcgen05 instructions take their operands from there)
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // x = hi + lo with hi = rna_tf32(x) and lo = rna_tf32(x - hi): both exactly representable in TF32 (low 13 mantissa
 // bits zero), so the tensor core's operand conversion is a no-op and the residual errors (lo*lo' dropped, rounding of
 // lo) are zero-mean ~2^-22 relative per product instead of a truncation bias.

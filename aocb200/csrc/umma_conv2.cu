@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
     const uint32_t raw0 = smem_u32(smem + Cfg::RAW_OFF);
     const uint32_t op0 = smem_u32(smem + Cfg::OP_OFF);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     // ---- tile decode: blockIdx.x -> (n, tile row, tile col), blockIdx.y -> output-channel tile
     const int tpi = p.tiles_x * p.tiles_y;
     const int n = blockIdx.x / tpi;
@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
         for (int c = 0; c < NC; ++c) acc[c] = 0.f;
         const int nchunks = (nIt + p.chunk - 1) / p.chunk;
         int b = 0;
-        uint32_t ph[2] = {0u, 0u};
+        uint32_t ph0 = 0u, ph1 = 0u;
         for (int ch = 0; ch < nchunks; ++ch) {
-            mbar_wait(MAIN_FULL(b), ph[b]);
-            ph[b] ^= 1u;
+            if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
+            else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -369,29 +369,31 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
             }
         }
     } else if (warp == 14) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = idesc_tf32(C2_BM, TN);
-            const uint32_t d_corr = tmem_base + 2 * TN;
-            int so = 0, b = 0, in_chunk = 0;
-            uint32_t po = 0, pe[2] = {0u, 0u};
-            for (int it = 0; it < nIt; ++it) {
-                mbar_wait(OP_FULL(so), po);
-                if (in_chunk == 0) {
-                    mbar_wait(MAIN_EMPTY(b), pe[b] ^ 1u);
-                    pe[b] ^= 1u;
-                }
-                tc_fence_after();
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+        const uint32_t idesc = idesc_tf32(C2_BM, TN);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t d_corr = tb + 2 * TN;
+        int so = 0, b = 0, in_chunk = 0;
+        uint32_t po = 0, pe0 = 0, pe1 = 0;
+        for (int it = 0; it < nIt; ++it) {
+            mbar_wait(OP_FULL(so), po);
+            if (in_chunk == 0) {
+                if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
+                else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
+            }
+            tc_fence_after();
+            const bool last = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
+            if (elect_one()) {
                 const uint32_t sa = op0 + so * Cfg::OP_BYTES;
                 const uint32_t sb = sa + Cfg::A_SMEM;
-                const uint32_t d_main = tmem_base + (uint32_t)(b * TN);
+                const uint32_t d_main = tb + (uint32_t)(b * TN);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
                     const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
                     const uint32_t acc_main = (in_chunk > 0 || ks > 0) ? 1u : 0u, acc_corr = (it > 0 || ks > 0) ? 1u : 0u;
                     if (TS) {
-                        const uint32_t ta_hi = tmem_base + Cfg::A_TMEM_COL + (uint32_t)(so * 32 + ks * 16), ta_lo = ta_hi + 8;
+                        const uint32_t ta_hi = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32 + ks * 16), ta_lo = ta_hi + 8;
                         mma_tf32_ts(d_main, ta_hi, dbh, idesc, acc_main);
                         mma_tf32_ts(d_corr, ta_lo, dbh, idesc, acc_corr);
                         mma_tf32_ts(d_corr, ta_hi, dbl, idesc, 1u);
@@ -404,13 +406,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                     }
                 }
                 mma_commit(OP_EMPTY(so));
-                if (++in_chunk == p.chunk || it == nIt - 1) {
-                    mma_commit(MAIN_FULL(b));
-                    b ^= 1;
-                    in_chunk = 0;
-                }
-                if (++so == C2_NO) { so = 0; po ^= 1u; }
+                if (last) mma_commit(MAIN_FULL(b));
             }
+            __syncwarp();
+            if (last) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
+            if (++so == C2_NO) { so = 0; po ^= 1u; }
         }
     }
     tc_fence_before();

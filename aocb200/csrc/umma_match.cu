@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
     __shared__ int seg[MAXO_ + 1];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, sp = blockIdx.y;
     const int rb0 = (int)((long long)nrb_total * sp / nsplit);
     const int rb1 = (int)((long long)nrb_total * (sp + 1) / nsplit);
@@ -121,35 +121,39 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rb1 > rb0) {
-            // ===== MMA issuer (single thread) =====
+        if (rb1 > rb0) {
+            // ===== MMA issuer: warp-uniform loop, one elected lane issues (operands stay in uniform registers) =====
             const uint32_t idesc = idesc_tf32(QB, RBK);
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             mbar_wait(A_FULL, 0);
             tc_fence_after();
             int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
+            uint32_t phase = 0, aph0 = 0, aph1 = 0;
             for (int rb = rb0; rb < rb1; ++rb) {
-                mbar_wait(TEMPTY(as), aphase ^ 1u);
+                if (as == 0) { mbar_wait(TEMPTY(0), aph0 ^ 1u); aph0 ^= 1u; }
+                else         { mbar_wait(TEMPTY(1), aph1 ^ 1u); aph1 ^= 1u; }
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)as * RBK;
+                const uint32_t d = tb + (uint32_t)as * RBK;
                 for (int ks = 0; ks < TC_KS; ++ks) {
                     mbar_wait(FULL(stage), phase);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sA) + ks * (A_BYTES / TC_KS);
-                    const uint32_t a_lo = a_hi + QB * KSTEP * 4;
-                    const uint32_t b_hi = smem_u32(sB) + stage * B_STAGE;
-                    const uint32_t b_lo = b_hi + RBK * KSTEP * 4;
-                    const uint64_t dah = smem_desc(a_hi, lbo, sbo), dal = smem_desc(a_lo, lbo, sbo);
-                    const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
-                    mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-                    mma_tf32(d, dah, dbl, idesc, 1u);
-                    mma_tf32(d, dah, dbh, idesc, 1u);
-                    mma_commit(EMPTY(stage));
+                    if (elect_one()) {
+                        const uint32_t a_hi = smem_u32(sA) + ks * (A_BYTES / TC_KS);
+                        const uint32_t a_lo = a_hi + QB * KSTEP * 4;
+                        const uint32_t b_hi = smem_u32(sB) + stage * B_STAGE;
+                        const uint32_t b_lo = b_hi + RBK * KSTEP * 4;
+                        const uint64_t dah = smem_desc(a_hi, lbo, sbo), dal = smem_desc(a_lo, lbo, sbo);
+                        const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
+                        mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                        mma_tf32(d, dah, dbl, idesc, 1u);
+                        mma_tf32(d, dah, dbh, idesc, 1u);
+                        mma_commit(EMPTY(stage));
+                        if (ks == TC_KS - 1) mma_commit(TFULL(as));
+                    }
+                    __syncwarp();
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
-                mma_commit(TFULL(as));
                 as ^= 1;
-                if (as == 0) aphase ^= 1u;
             }
         }
     } else if (warp >= 4) {
