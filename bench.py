@@ -38,7 +38,9 @@ def peaks():
             p = json.load(f)
         return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"], "src": "measured"}
     except Exception:
-        return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+        # MEASURED_PEAKS.json is driver-written and absent from this checkout: these are the values the driver measured on
+        # this pool's B200s at the start of round 1, as recorded in SURVEY.md section 5 / 8d
+        return {"hbm": 6546.6, "tensor_burst": 1661.7, "tensor": 1398.2, "src": "measured (SURVEY.md copy of MEASURED_PEAKS.json)"}
 
 
 class ClockSampler:
@@ -164,7 +166,9 @@ def kernel_profile(model, frames, first, device, n_frames):
     from aocb200.lib import lib
     L = lib()
     np.random.seed(77)
-    st = Stepper(model, frames, first, K_OBJ, device, False)
+    eng = model.engine()
+    graphs, eng.use_graphs = eng.use_graphs, False      # per-launch events need plain launches: same kernels, same
+    st = Stepper(model, frames, first, K_OBJ, device, False)   # shapes, just not replayed from the captured graphs
     for _ in range(2):
         st.step()
     L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_kmeans_proxies_f32": []}
@@ -172,6 +176,7 @@ def kernel_profile(model, frames, first, device, n_frames):
         st.step()
     torch.cuda.synchronize()
     prof, L.profile = L.profile, None
+    eng.use_graphs = graphs
     out = {}
     conv = prof["aoc_conv2d_nhwc_tc"]
     if conv:
