@@ -15,12 +15,12 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace aoc
 
-namespace aoc { extern int g_conv_ts; }
+namespace aoc { extern int g_conv_chunk; }
 
 extern "C" int aoc_version(void) { return 101; }
 
 extern "C" int aoc_set_option(const char* key, int value) {
-    if (key && !strcmp(key, "conv_ts")) { aoc::g_conv_ts = value ? 1 : 0; return AOC_OK; }
+    if (key && !strcmp(key, "conv_chunk") && value > 0) { aoc::g_conv_chunk = value; return AOC_OK; }
     aoc::set_error("aoc_set_option: unknown option '%s'", key ? key : "(null)");
     return AOC_EINVAL;
 }

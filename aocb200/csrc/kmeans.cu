@@ -9,8 +9,9 @@
 //   * returned labels are those of the last round (computed against the code book before its final update);
 //   * centroid_avg[j] = mean_{t : label_i[t] == j} B[t], B = ALL-object bank in natural order (the reference's
 //     indexing quirk), only for non-empty labels.
-// HBM/L2-bound streaming kernels: one thread per row for the assignment (centroids broadcast from shared
-// memory), fixed-order per-block partial sums + a second-stage reduction (deterministic), no tensor cores.
+// HBM/L2-bound streaming kernels: row tiles staged in shared memory with coalesced 128-bit loads, sequential-order
+// dot products per row (the order of the reference's BLAS call, so near ties break the same way), fixed-order tile sums +
+// a warp-parallel second-stage reduction (deterministic); no tensor cores, no atomics.
 #include "common.cuh"
 
 namespace aoc {
@@ -19,7 +20,6 @@ constexpr int MAXO = AOC_MAX_OBJECTS;
 constexpr int EMB = 100;
 constexpr int EMB4 = 25;
 constexpr int KM_K = AOC_KMEANS_MAX_K;   // 16
-constexpr int KM_PTS = 256;              // rows per block
 
 // cent: [O][KM_K][EMB]
 __global__ void kmeans_init_kernel(const float* __restrict__ S, const int* __restrict__ meta,
@@ -36,106 +36,133 @@ __global__ void kmeans_init_kernel(const float* __restrict__ S, const int* __res
     }
 }
 
-// ASSIGN: compute labels of this block's rows against cent, store them.  Then accumulate per-label sums of
-// (INDIRECT ? S[nat2sorted[t]] : S[seg + t]) in row order into part[o][b][KM_K][EMB], counts into pcnt[o][b][KM_K].
+// One Lloyd half-step over a tile of KM_TILE rows of one object (block = 256 threads):
+//   1. the tile is staged in shared memory with coalesced 128-bit loads (row stride 101 floats: conflict-free both for
+//      the row-per-thread reads of step 2 and the channel-per-thread reads of step 3);
+//   2. ASSIGN: thread (row, half) accumulates the dot products with centroids 8*half .. 8*half+7 SEQUENTIALLY over the
+//      channels, fma by fma -- the summation order of a BLAS sgemm element, i.e. of scipy's vq, so near-tie rows get the
+//      same label as in the reference; distance (-2 x.c + |x|^2) + |c|^2; lowest index wins ties;
+//   3. per-label column sums: thread (label parity, channel) walks the rows in order and adds into its own column of a
+//      shared accumulator (fixed order, no atomics -> deterministic).
+// INDIRECT (centroid_avg pass, matching.py:589): label t of the object selects row nat2sorted[t] of the ALL-object bank.
+// part[o][b][KM_K][EMB] / pcnt[o][b][KM_K] receive the tile's per-label sums and counts.
+constexpr int KM_TILE = 128;
+constexpr int KM_LD = 101;
+constexpr int KM_SMEM = (KM_TILE * KM_LD + EMB * KM_K + KM_K * EMB) * 4;   // tile + centroids + accumulators
+
 template <bool ASSIGN, bool INDIRECT>
 __global__ void __launch_bounds__(256) kmeans_step_kernel(const float* __restrict__ S, const int* __restrict__ meta,
-                                                           const int* __restrict__ kk,
-                                                           const float* __restrict__ cent,
+                                                           const int* __restrict__ kk, const float* __restrict__ cent,
                                                            const int* __restrict__ nat2sorted,
                                                            int* __restrict__ labels /*[sorted rows]*/,
                                                            float* __restrict__ part, int* __restrict__ pcnt,
                                                            int nb_max) {
-    __shared__ __align__(16) float Cs[EMB][KM_K];
+    extern __shared__ __align__(16) float km_sm[];
+    float* tile = km_sm;                                   // [KM_TILE][KM_LD]
+    float* Cs = tile + KM_TILE * KM_LD;                    // [EMB][KM_K]
+    float* acc = Cs + EMB * KM_K;                          // [KM_K][EMB]
     __shared__ float c2[KM_K];
-    __shared__ int lab[KM_PTS];
-    __shared__ float acc[2][KM_K][EMB];
+    __shared__ int lab[KM_TILE];
+    __shared__ float bd_hi[KM_TILE];
+    __shared__ int bj_hi[KM_TILE];
     const int o = blockIdx.y, b = blockIdx.x;
     const int n_o = meta[o];
     const int k = kk[o];
-    const int t0 = b * KM_PTS;
+    const int t0 = b * KM_TILE;
     if (t0 >= n_o || k <= 0) return;
     const int seg = meta[MAXO + o];
-    const int tid = threadIdx.x;
-    const int t = t0 + tid;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nrow = min(KM_TILE, n_o - t0);
 
+    // ---- 1. stage the tile: warp w loads rows w, w+8, ... (25 lanes x 16 B = one 400 B row per instruction)
+    for (int r = warp; r < nrow; r += 8) {
+        const int srow = INDIRECT ? __ldg(nat2sorted + t0 + r) : (seg + t0 + r);
+        if (lane < EMB4) {
+            float4 v = ldg4(S + (size_t)srow * EMB + lane * 4);
+            float* d = tile + r * KM_LD + lane * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
     if (ASSIGN) {
         for (int i = tid; i < KM_K * EMB; i += 256) {
             int j = i / EMB, c = i - j * EMB;
-            Cs[c][j] = cent[(size_t)o * KM_K * EMB + i];
+            Cs[c * KM_K + j] = cent[(size_t)o * KM_K * EMB + i];
         }
-        __syncthreads();
+    }
+    for (int i = tid; i < KM_K * EMB; i += 256) acc[i] = 0.f;
+    __syncthreads();
+    if (ASSIGN) {
         if (tid < KM_K) {
             float s = 0.f;
-            for (int c = 0; c < EMB; ++c) s = fmaf(Cs[c][tid], Cs[c][tid], s);
+            for (int c = 0; c < EMB; ++c) s = fmaf(Cs[c * KM_K + tid], Cs[c * KM_K + tid], s);
             c2[tid] = s;
         }
         __syncthreads();
-        int best = 0;
-        if (t < n_o) {
-            const float* row = S + (size_t)(seg + t) * EMB;
-            float dot[KM_K];
+        // ---- 2. assignment: thread (row, half)
+        const int row = tid & (KM_TILE - 1), half = tid >> 7;
+        float bd = INFINITY;
+        int bj = half * 8;
+        if (row < nrow) {
+            const float* xr = tile + row * KM_LD;
+            const float4* cr = reinterpret_cast<const float4*>(Cs + half * 8);
+            float dot[8];
 #pragma unroll
-            for (int j = 0; j < KM_K; ++j) dot[j] = 0.f;
+            for (int j = 0; j < 8; ++j) dot[j] = 0.f;
             float x2 = 0.f;
-#pragma unroll 5
-            for (int c4 = 0; c4 < EMB4; ++c4) {
-                float4 v = ldg4(row + c4 * 4);
-                float xs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    x2 = fmaf(xs[e], xs[e], x2);
-                    const float4* cr = reinterpret_cast<const float4*>(&Cs[c4 * 4 + e][0]);
-#pragma unroll
-                    for (int j4 = 0; j4 < KM_K / 4; ++j4) {
-                        float4 cc = cr[j4];
-                        dot[j4 * 4 + 0] = fmaf(xs[e], cc.x, dot[j4 * 4 + 0]);
-                        dot[j4 * 4 + 1] = fmaf(xs[e], cc.y, dot[j4 * 4 + 1]);
-                        dot[j4 * 4 + 2] = fmaf(xs[e], cc.z, dot[j4 * 4 + 2]);
-                        dot[j4 * 4 + 3] = fmaf(xs[e], cc.w, dot[j4 * 4 + 3]);
-                    }
-                }
+#pragma unroll 4
+            for (int c = 0; c < EMB; ++c) {
+                const float x = xr[c];
+                x2 = fmaf(x, x, x2);
+                const float4 ca = cr[c * (KM_K / 4)], cb = cr[c * (KM_K / 4) + 1];
+                dot[0] = fmaf(x, ca.x, dot[0]); dot[1] = fmaf(x, ca.y, dot[1]);
+                dot[2] = fmaf(x, ca.z, dot[2]); dot[3] = fmaf(x, ca.w, dot[3]);
+                dot[4] = fmaf(x, cb.x, dot[4]); dot[5] = fmaf(x, cb.y, dot[5]);
+                dot[6] = fmaf(x, cb.z, dot[6]); dot[7] = fmaf(x, cb.w, dot[7]);
             }
-            float bd = INFINITY;
 #pragma unroll
-            for (int j = 0; j < KM_K; ++j) {
-                float d = (dot[j] * -2.0f + x2) + c2[j];
-                if (j < k && d < bd) { bd = d; best = j; }
+            for (int j = 0; j < 8; ++j) {
+                const int jj = half * 8 + j;
+                const float d = (dot[j] * -2.0f + x2) + c2[jj];
+                if (jj < k && d < bd) { bd = d; bj = jj; }
             }
-            labels[seg + t] = best;
         }
-        lab[tid] = (t < n_o) ? best : -1;
+        if (half == 1) { bd_hi[row] = bd; bj_hi[row] = bj; }
+        __syncthreads();
+        if (half == 0) {
+            int best = -1;
+            if (row < nrow) {
+                if (bd_hi[row] < bd) bj = bj_hi[row];          // strict: the lower index wins ties
+                best = bj;
+                labels[seg + t0 + row] = best;
+            }
+            lab[row] = best;
+        }
     } else {
-        lab[tid] = (t < n_o) ? labels[seg + t] : -1;
+        if (tid < KM_TILE) lab[tid] = (tid < nrow) ? labels[seg + t0 + tid] : -1;
     }
-    for (int i = tid; i < 2 * KM_K * EMB; i += 256) (&acc[0][0][0])[i] = 0.f;
     __syncthreads();
-    // fixed-order accumulation: thread (half, c) walks its half of the block's rows in order
+    // ---- 3. per-label column sums in row order: thread (label parity g, channel c)
     {
-        int half = tid >> 7, c = tid & 127;
+        const int g = tid >> 7, c = tid & 127;
         if (c < EMB) {
-            int pbeg = half * (KM_PTS / 2), pend = pbeg + KM_PTS / 2;
-            for (int p = pbeg; p < pend; ++p) {
-                int l = lab[p];
-                if (l < 0) break;
-                int srow = INDIRECT ? nat2sorted[t0 + p] : (seg + t0 + p);
-                acc[half][l][c] += __ldg(S + (size_t)srow * EMB + c);
+            for (int r = 0; r < nrow; ++r) {
+                const int l = lab[r];
+                if ((l & 1) == g) acc[l * EMB + c] += tile[r * KM_LD + c];
             }
         }
     }
     __syncthreads();
-    size_t pbase = ((size_t)o * nb_max + b) * KM_K;
-    for (int i = tid; i < KM_K * EMB; i += 256) {
-        int j = i / EMB, c = i - j * EMB;
-        part[pbase * EMB + i] = acc[0][j][c] + acc[1][j][c];
-    }
+    const size_t pbase = ((size_t)o * nb_max + b) * KM_K;
+    for (int i = tid; i < KM_K * EMB; i += 256) part[pbase * EMB + i] = acc[i];
     if (tid < KM_K) {
         int n = 0;
-        for (int p = 0; p < KM_PTS; ++p) n += (lab[p] == tid);
+        for (int r = 0; r < nrow; ++r) n += (lab[r] == tid);
         pcnt[pbase + tid] = n;
     }
 }
 
+// Second stage, one block per (cluster j, object o): warp w sums the slabs b = w, w+8, ... (lanes over channels,
+// 128-bit loads), the 8 warps are combined in a fixed order in double precision.
 // MODE 0: Lloyd update (cent[j] = sum/cnt, empty keeps previous).  MODE 1: write centroid_avg + validity.
 // P: [O][AOC_PROXY_SLOTS][EMB], pvalid: [O][AOC_PROXY_SLOTS]
 template <int MODE>
@@ -143,29 +170,43 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
                                                              const int* __restrict__ pcnt,
                                                              const int* __restrict__ meta,
                                                              const int* __restrict__ kk, int nb_max,
-                                                             float* __restrict__ cent, float* __restrict__ P,
-                                                             int* __restrict__ pvalid) {
-    const int o = blockIdx.y;
+                                                             int rows_per_block, float* __restrict__ cent,
+                                                             float* __restrict__ P, int* __restrict__ pvalid) {
+    __shared__ double sm[8][EMB];
+    __shared__ int sn[8];
+    const int j = blockIdx.x, o = blockIdx.y;
     const int n_o = meta[o];
     const int k = kk[o];
-    const int nb = (n_o + KM_PTS - 1) / KM_PTS;
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= KM_K * EMB) return;
-    int j = i / EMB, c = i - j * EMB;
-    double s = 0.0;
-    long long n = 0;
+    const int nb = (n_o + rows_per_block - 1) / rows_per_block;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int n = 0;
     if (j < k) {
-        for (int b = 0; b < nb; ++b) {
-            size_t pbase = ((size_t)o * nb_max + b) * KM_K;
-            s += (double)part[pbase * EMB + i];
-            n += pcnt[pbase + j];
+        for (int b = warp; b < nb; b += 8) {
+            const size_t pbase = ((size_t)o * nb_max + b) * KM_K + j;
+            if (lane < EMB4) {
+                float4 v = ldg4(part + pbase * EMB + lane * 4);
+                s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+            }
+            n += __ldg(pcnt + pbase);
         }
     }
+    if (lane < EMB4) {
+        sm[warp][lane * 4 + 0] = s0; sm[warp][lane * 4 + 1] = s1; sm[warp][lane * 4 + 2] = s2; sm[warp][lane * 4 + 3] = s3;
+    }
+    if (lane == 0) sn[warp] = n;
+    __syncthreads();
+    const int c = threadIdx.x;
+    if (c >= EMB) return;
+    double s = 0.0;
+    long long cntj = 0;
+    for (int w = 0; w < 8; ++w) { s += sm[w][c]; cntj += sn[w]; }
+    const int i = j * EMB + c;
     if (MODE == 0) {
-        if (j < k && n > 0) cent[(size_t)o * KM_K * EMB + i] = (float)s / (float)n;
+        if (j < k && cntj > 0) cent[(size_t)o * KM_K * EMB + i] = (float)s / (float)cntj;
     } else {
-        bool ok = (j < k) && n > 0;
-        P[((size_t)o * AOC_PROXY_SLOTS + 16 + j) * EMB + c] = ok ? (float)s / (float)n : 0.f;
+        bool ok = (j < k) && cntj > 0;
+        P[((size_t)o * AOC_PROXY_SLOTS + 16 + j) * EMB + c] = ok ? (float)s / (float)cntj : 0.f;
         P[((size_t)o * AOC_PROXY_SLOTS + j) * EMB + c] = (j < k) ? cent[(size_t)o * KM_K * EMB + i] : 0.f;
         if (c == 0) {
             pvalid[o * AOC_PROXY_SLOTS + j] = (j < k) ? 1 : 0;
@@ -174,12 +215,15 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
     }
 }
 
+static int km_rows_per_block(int) { return KM_TILE; }
+
 }  // namespace aoc
 
 using namespace aoc;
 
 extern "C" size_t aoc_kmeans_workspace_bytes(int max_rows_per_object, int O) {
-    size_t nb = (size_t)cdiv(max_rows_per_object > 0 ? max_rows_per_object : 1, KM_PTS);
+    int m = max_rows_per_object > 0 ? max_rows_per_object : 1;
+    size_t nb = (size_t)cdiv(m, km_rows_per_block(m));
     return (size_t)O * nb * KM_K * (EMB * sizeof(float) + sizeof(int)) + 256;
 }
 
@@ -194,17 +238,25 @@ extern "C" int aoc_kmeans_proxies_f32(const float* S, const int* meta, const int
                   "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO && iters >= 1, "bad dims");
     AOC_CHECK_ARG(ws_bytes >= aoc_kmeans_workspace_bytes(max_rows_per_object, O), "workspace too small");
-    int nb = cdiv(max_rows_per_object > 0 ? max_rows_per_object : 1, KM_PTS);
+    const int m = max_rows_per_object > 0 ? max_rows_per_object : 1;
+    const int rpb = km_rows_per_block(m);
+    int nb = cdiv(m, rpb);
     float* part = (float*)workspace;
     int* pcnt = (int*)(part + (size_t)O * nb * KM_K * EMB);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kmeans_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM);
+        cudaFuncSetAttribute(kmeans_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM);
+        attr = true;
+    }
     kmeans_init_kernel<<<O, 256, 0, stream>>>(S, meta, kk, init_idx, cent);
-    dim3 gs(nb, O), gr(cdiv(KM_K * EMB, 256), O);
+    dim3 gs(nb, O), gr(KM_K, O);
     for (int it = 0; it < iters; ++it) {
-        kmeans_step_kernel<true, false><<<gs, 256, 0, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
-        kmeans_reduce_kernel<0><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, cent, P, pvalid);
+        kmeans_step_kernel<true, false><<<gs, 256, KM_SMEM, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
+        kmeans_reduce_kernel<0><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
     }
     // centroid_avg: same labels, rows taken from the all-object bank in natural order (matching.py:589)
-    kmeans_step_kernel<false, true><<<gs, 256, 0, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
-    kmeans_reduce_kernel<1><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, cent, P, pvalid);
+    kmeans_step_kernel<false, true><<<gs, 256, KM_SMEM, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
+    kmeans_reduce_kernel<1><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
     return launch_status("aoc_kmeans_proxies_f32");
 }

@@ -6,14 +6,18 @@
 // (GroupNorm apply + ReLU, GCT / IA gate) fused into the operand path.
 //
 // Data flow of one CTA (128 output pixels x TN output channels, K consumed in stages of 16 input channels of one tap):
-//   warp 12  TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][16] (zero fill = conv padding,
-//            element strides = conv stride, 64B swizzle) into an 8-deep ring
-//   warps 0-3  transform: raw -> (optional a*x+b, ReLU, padding mask) -> 3xTF32 split hi = rna(x), lo = rna(x - hi)
-//            -> tcgen05 K-major core-matrix layout in the 4-deep operand ring (generic proxy -> fence.proxy.async)
-//   warp 13  TMA bulk copies of the pre-split weight image into the same operand ring stage
-//   warp 14  one thread issues tcgen05.mma kind::tf32:  hi*hi -> MAIN accumulator, lo*hi + hi*lo -> CORR accumulator
+//   warp 12  TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][32 channels] (zero fill = conv padding,
+//            element strides = conv stride, 128B swizzle) into a 4-deep ring; one box feeds two operand stages
+//   warps 0-3  transform (thread = pixel = TMEM lane): raw -> (optional a*x+b, ReLU, padding mask) -> 3xTF32 split
+//            hi = rna(x), lo = rna(x - hi) -> tcgen05.st into a 4-deep operand ring in TENSOR memory
+//   warp 13  TMA bulk copies of the pre-split weight image into the shared-memory operand ring
+//   warp 14  warp-uniform loop, one elected lane issues tcgen05.mma kind::tf32 with the A operand from TMEM:
+//            hi*hi -> MAIN accumulator, lo*hi + hi*lo -> CORR accumulator
 //   warps 4-11 drain: every `chunk` stages the MAIN accumulator (double buffered in TMEM) is read with tcgen05.ld and
 //            added to fp32 registers with round-to-nearest; epilogue adds CORR, bias, residual, ReLU; 128-bit stores.
+// Shared memory only carries the raw patch and the weights: with both operands in shared memory the 128 B/clk port was
+// the limit (measured 821 us vs 764 us on the largest layer), and the per-MMA operand set-up must come from uniform
+// registers (a divergent single-thread issue loop cost ~14 instructions per MMA: 764 us -> 509 us once warp-uniform).
 //
 // Why the chunked accumulation: the tensor core adds into its fp32 accumulator with truncation, a systematic
 // -0.5 ulp per MMA.  Over K = 2304 ... 18432 that bias reaches 1e-4 relative and broke the 1e-3 logit parity
@@ -29,11 +33,11 @@ namespace aoc {
 using namespace umma;
 
 constexpr int C2_BM = 128;
-constexpr int C2_KC = 16;                               // input channels per stage (2 k-steps of 8)
-constexpr int C2_NR = 8;                                // raw ring depth
-constexpr int C2_NO = 4;                                // operand ring depth
-constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_KC * 4;    // 8192
-constexpr uint32_t C2_A_BYTES = 2 * C2_RAW_BYTES;       // hi + lo
+constexpr int C2_KC = 16;                               // input channels per operand stage (2 k-steps of 8)
+constexpr int C2_RKC = 32;                              // input channels per TMA box (128-byte rows)
+constexpr int C2_NO = 4;                                // activation operand ring depth (TMEM, 32 columns per stage)
+constexpr int C2_NB = 8;                                // weight ring depth (shared memory)
+constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_RKC * 4;   // 16384
 constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
 constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
 constexpr int C2_MAX_AFFINE_C = 1024;
@@ -43,7 +47,8 @@ struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
     int N, H, W, Cin, Ho, Wo, Cout, ldy, ldres, kw, stride, pad, dil, relu, in_relu;
     int tw_log2, th, tiles_x, tiles_y;
-    int ncc, nIt, chunk;
+    int ncc, nIt, chunk, taps;
+    int tiles_n, total_tiles;
     int vec_out;
 };
 
@@ -55,208 +60,175 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-// TS = true: the split activation operand lives in TENSOR memory (written with tcgen05.st, read by tcgen05.mma as the A
-// operand), so shared memory only carries the raw patch and the weights -- the SS variant (both operands in shared
-// memory) is bound by the 128 B/clk shared-memory port at about half the tensor rate.
-template <int TN, bool TS>
+// Ring depths are sized for LATENCY, not bandwidth: a weight chunk is requested when the MMAs of the stage it replaces
+// retire and must have landed (L2 round trip ~1.5k cycles) before its own MMAs are due, so the weight ring is 8 stages
+// deep (with 4 the kernel ran at ~600 cycles per stage regardless of the tile width: 4 stages per round trip).
+template <int TN>
 struct C2Cfg {
+    static constexpr int NR = TN <= 64 ? 8 : 4;              // raw activation ring depth (128 pixels x 32 channels each)
     static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
-    static constexpr uint32_t A_SMEM = TS ? 0u : C2_A_BYTES;
-    static constexpr uint32_t OP_BYTES = A_SMEM + B_BYTES;
     static constexpr uint32_t RAW_OFF = 0;
-    static constexpr uint32_t OP_OFF = C2_NR * C2_RAW_BYTES;
-    static constexpr uint32_t TAB_OFF = OP_OFF + C2_NO * OP_BYTES;
+    static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
+    static constexpr uint32_t TAB_OFF = OP_OFF + C2_NB * B_BYTES;
     static constexpr uint32_t BAR_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
-    static constexpr uint32_t TMEM_COLS = TS ? 512 : (TN <= 64 ? 256 : 512);
-    static constexpr uint32_t A_TMEM_COL = 3 * TN;           // TS: ring of C2_NO stages x 32 columns
+    static constexpr uint32_t TMEM_COLS = 512;
+    static constexpr int NCB = TN <= 64 ? 2 : 1;             // CORR accumulators: double buffered across tiles when they fit
+    static constexpr uint32_t A_TMEM_COL = (2 + NCB) * TN;   // ring of C2_NO stages x 32 columns behind MAIN[2] + CORR[NCB]
 };
 
-template <int TN, bool TS>
+template <int TN>
 __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
-    using Cfg = C2Cfg<TN, TS>;
+    using Cfg = C2Cfg<TN>;
+    constexpr int C2_NR = Cfg::NR;
+    constexpr int NCB = Cfg::NCB;                            // CORR accumulator buffers (2 when TMEM allows)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* tab_a = reinterpret_cast<float*>(smem + Cfg::TAB_OFF);
     float* tab_b = tab_a + C2_MAX_AFFINE_C;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 60);
     const uint32_t bar0 = smem_u32(bars);
     auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
     auto RAW_EMPTY = [&](int s) { return bar0 + 8u * (C2_NR + s); };
-    auto OP_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + s); };
+    auto OP_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + s); };                       // activation operand (TMEM)
     auto OP_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + C2_NO + s); };
-    auto MAIN_FULL = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + b); };
-    auto MAIN_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 + b); };
+    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + s); };            // weight operand (smem)
+    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + C2_NB + s); };
+    auto MAIN_FULL = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + b); };
+    auto MAIN_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + 2 + b); };
+    auto CORR_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + 4 + b); };
     const uint32_t raw0 = smem_u32(smem + Cfg::RAW_OFF);
     const uint32_t op0 = smem_u32(smem + Cfg::OP_OFF);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-    // ---- tile decode: blockIdx.x -> (n, tile row, tile col), blockIdx.y -> output-channel tile
-    const int tpi = p.tiles_x * p.tiles_y;
-    const int n = blockIdx.x / tpi;
-    const int trem = blockIdx.x - n * tpi;
-    const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
     const int tw_mask = (1 << p.tw_log2) - 1;
-    const int ho0 = tyi * p.th, wo0 = txi << p.tw_log2;
-    const int n0 = blockIdx.y * TN;
+    const int tpi = p.tiles_x * p.tiles_y;
     const bool affine = p.in_a != nullptr || p.in_b != nullptr || p.in_relu;
+    const int nIt = p.nIt;
+    // persistent CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; t -> (pixel tile, output-channel tile) with the
+    // channel tile fastest, so CTAs running side by side share the activation patch in L2.  Every role walks the same
+    // tile sequence and the rings keep flowing across tile boundaries (the producers run ahead into the next tile).
+    struct Tile { int n, ho0, wo0, n0; };
+    auto decode = [&](int t) {
+        Tile tl;
+        const int mt = t / p.tiles_n;
+        tl.n0 = (t - mt * p.tiles_n) * TN;
+        tl.n = mt / tpi;
+        const int trem = mt - tl.n * tpi;
+        const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+        tl.ho0 = tyi * p.th;
+        tl.wo0 = txi << p.tw_log2;
+        return tl;
+    };
 
     if (warp == 15 && lane == 0) {
         for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
-        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 5); mbar_init(OP_EMPTY(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); }
+        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1); }
+        for (int s = 0; s < C2_NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); }
         fence_barrier_init();
     }
     if (warp == 14) {
         tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
         tmem_relinquish();
     }
-    if (affine) {
-        const int cpad = p.ncc * C2_KC;
-        for (int c = threadIdx.x; c < cpad; c += C2_THREADS) {
-            const bool ok = c < p.Cin;
-            tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)n * p.Cin + c) : 1.f) : 0.f;
-            tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)n * p.Cin + c) : 0.f;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nIt = p.nIt;
 
-    if (warp < 4 && TS) {
-        // ===== transform warps (TS): thread <-> pixel row <-> TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
+    if (warp < 4) {
+        // ===== transform warps: thread <-> pixel row <-> TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
         const int pp = threadIdx.x;
         const int ty = pp >> p.tw_log2, tx = pp & tw_mask;
-        const int hb = (ho0 + ty) * p.stride - p.pad, wb = (wo0 + tx) * p.stride - p.pad;
-        const uint32_t src_row = (uint32_t)(pp * 64);
-        const uint32_t sw = (uint32_t)((pp >> 1) & 3);                       // TMA SWIZZLE_64B
+        const uint32_t src_row = (uint32_t)(pp * 128);
+        const uint32_t sw = (uint32_t)(pp & 7);                              // TMA SWIZZLE_128B: 16 B chunk ^= row % 8
         const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + Cfg::A_TMEM_COL;
         const bool need_mask = p.in_b != nullptr;
         int sr = 0, so = 0;
         uint32_t pr = 0, po = 0;
-        int tap = 0, cc = 0;
+        int tab_n = -1;
         float v[16];
-        auto load_raw = [&]() {         // waits for raw stage sr and pulls this thread's 16 channels into registers
-            mbar_wait(RAW_FULL(sr), pr);
+        // channel chunk cc_ of a tap lives in raw stage sr, half cc_ & 1 (a fresh stage is awaited on even chunks)
+        auto load_raw = [&](int cc_) {
+            if ((cc_ & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
             const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
+            const uint32_t c8 = (uint32_t)(cc_ & 1) * 4u;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
-                             : "r"(rawb + ((j ^ sw) << 4)));
+                             : "r"(rawb + (((c8 + j) ^ sw) << 4)));
         };
-        if (nIt > 0) load_raw();
-        for (int it = 0; it < nIt; ++it) {
-            if (affine) {
-                bool ok = true;
-                if (need_mask) {
-                    const int r = tap / p.kw, s = tap - r * p.kw;
-                    ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s * p.dil) < (unsigned)p.W;
+        bool primed = false;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const Tile tl = decode(t);
+            const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
+            if (affine && tl.n != tab_n) {
+                // per-(sample, channel) coefficient table of this image; only the transform warps touch it
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int cpad = p.ncc * C2_KC;
+                for (int c = pp; c < cpad; c += 128) {
+                    const bool ok = c < p.Cin;
+                    tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)tl.n * p.Cin + c) : 1.f) : 0.f;
+                    tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)tl.n * p.Cin + c) : 0.f;
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
-                    const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
-                    v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
-                    v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
-                }
-                if (p.in_relu) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-                }
-                if (!ok) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = 0.f;
-                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                tab_n = tl.n;
             }
-            // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
-            float o[32];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                float h, l;
-                split_tf32(v[e], h, l);
-                o[(e >> 3) * 16 + (e & 7)] = h;
-                o[(e >> 3) * 16 + 8 + (e & 7)] = l;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(RAW_EMPTY(sr));          // raw stage consumed (values are in registers)
-            if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
-            if (it + 1 < nIt) load_raw();                       // next stage's loads fly while this one is stored
-            mbar_wait(OP_EMPTY(so), po ^ 1u);
-            tc_fence_after();
-            tmem_st32(a_lane + (uint32_t)(so * 32), o);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(OP_FULL(so));
-            if (++so == C2_NO) { so = 0; po ^= 1u; }
-            if (++cc == p.ncc) { cc = 0; ++tap; }
-        }
-    } else if (warp < 4) {
-        // ===== transform warps: raw fp32 patch -> (affine, relu, mask) -> hi/lo operand blocks =====
-        const int t = threadIdx.x;
-        const int j = (t >> 3) & 3;                       // 16-byte channel granule of the stage (4 floats)
-        const int pbase = (t & 7) + 8 * (t >> 5);         // pixels pbase + 32 q
-        int hb[4], wb[4];
-        uint32_t src_off[4], dst_off[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int pp = pbase + 32 * q;
-            const int ty = pp >> p.tw_log2, tx = pp & tw_mask;
-            hb[q] = (ho0 + ty) * p.stride - p.pad;
-            wb[q] = (wo0 + tx) * p.stride - p.pad;
-            src_off[q] = (uint32_t)(pp * 64 + ((j ^ ((pp >> 1) & 3)) << 4));        // TMA SWIZZLE_64B
-            dst_off[q] = (uint32_t)((j >> 1) * (2 * C2_RAW_BYTES / 2) + (pp >> 3) * 256 + (j & 1) * 128 + (pp & 7) * 16);
-        }
-        const bool need_mask = p.in_b != nullptr;
-        int sr = 0, so = 0;
-        uint32_t pr = 0, po = 0;
-        int tap = 0, cc = 0;
-        for (int it = 0; it < nIt; ++it) {
-            mbar_wait(RAW_FULL(sr), pr);
-            mbar_wait(OP_EMPTY(so), po ^ 1u);
-            const uint32_t rawb = raw0 + sr * C2_RAW_BYTES;
-            const uint32_t opb = op0 + so * Cfg::OP_BYTES;
-            float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int dh = 0, dw = 0;
-            if (affine) {
-                a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
-                b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
-                const int r = tap / p.kw, s = tap - r * p.kw;
-                dh = r * p.dil; dw = s * p.dil;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 v;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rawb + src_off[q]));
+            if (!primed) { load_raw(0); primed = true; }
+            const bool more_tiles = t + (int)gridDim.x < p.total_tiles;
+            int tap = 0, cc = 0;
+            for (int it = 0; it < nIt; ++it) {
                 if (affine) {
-                    v.x = fmaf(v.x, a4.x, b4.x); v.y = fmaf(v.y, a4.y, b4.y);
-                    v.z = fmaf(v.z, a4.z, b4.z); v.w = fmaf(v.w, a4.w, b4.w);
-                    if (p.in_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    bool ok = true;
                     if (need_mask) {
-                        const bool ok = (unsigned)(hb[q] + dh) < (unsigned)p.H && (unsigned)(wb[q] + dw) < (unsigned)p.W;
-                        if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int r = tap / p.kw, s = tap - r * p.kw;
+                        ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s * p.dil) < (unsigned)p.W;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
+                        const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
+                        v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
+                        v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
+                    }
+                    if (p.in_relu) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+                    }
+                    if (!ok) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = 0.f;
                     }
                 }
-                float h0, h1, h2, h3, l0, l1, l2, l3;
-                split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
-                const uint32_t d = opb + dst_off[q];
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d), "f"(h0), "f"(h1), "f"(h2), "f"(h3) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d + C2_RAW_BYTES / 2), "f"(l0), "f"(l1), "f"(l2), "f"(l3) : "memory");
+                // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
+                float o[32];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float h, l;
+                    split_tf32(v[e], h, l);
+                    o[(e >> 3) * 16 + (e & 7)] = h;
+                    o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                }
+                __syncwarp();
+                if ((cc & 1) || cc == p.ncc - 1) {              // second half (or an odd tail) read: raw stage is free
+                    if (lane == 0) mbar_arrive(RAW_EMPTY(sr));
+                    if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                }
+                if (++cc == p.ncc) { cc = 0; ++tap; }
+                // the next stage's loads fly while this one is stored (the first stage of the next tile included)
+                if (it + 1 < nIt || more_tiles) load_raw(it + 1 < nIt ? cc : 0);
+                mbar_wait(OP_EMPTY(so), po ^ 1u);
+                tc_fence_after();
+                tmem_st32(a_lane + (uint32_t)(so * 32), o);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(OP_FULL(so));
+                if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(OP_FULL(so));
-                mbar_arrive(RAW_EMPTY(sr));
-            }
-            if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
-            if (++so == C2_NO) { so = 0; po ^= 1u; }
-            if (++cc == p.ncc) { cc = 0; ++tap; }
         }
     } else if (warp < 12) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
@@ -264,153 +236,168 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
         const int dwp = warp - 4;
         const int q = dwp & 3, half = dwp >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
-        float acc[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] = 0.f;
         const int nchunks = (nIt + p.chunk - 1) / p.chunk;
-        int b = 0;
+        const int m = q * 32 + lane;
+        const int ty = m >> p.tw_log2, tx = m & tw_mask;
+        int b = 0, cb = 0;
         uint32_t ph0 = 0u, ph1 = 0u;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
-            else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
-            tc_fence_after();
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const Tile tl = decode(t);
+            float acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
+                else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < NC; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tlane + (uint32_t)(b * TN + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
+                b ^= 1;
+            }
+            // all MMAs of the tile (including CORR) are complete once its last MAIN_FULL has fired
 #pragma unroll
             for (int c0 = 0; c0 < NC; c0 += 32) {
                 float v[32];
-                tmem_ld32(tlane + (uint32_t)(b * TN + c0), v);
+                tmem_ld32(tlane + (uint32_t)((2 + cb) * TN + c0), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
-            b ^= 1;
-        }
-        // all MMAs (including CORR) are complete once the last MAIN_FULL has fired
+            if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
+            if (NCB == 2) cb ^= 1;
+            const int ho = tl.ho0 + ty, wo = tl.wo0 + tx;
+            if (ho < p.Ho && wo < p.Wo) {
+                const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
+                const int cbase = tl.n0 + half * NC;
+                float* dst = p.y + pix * p.ldy + cbase;
+                const float* rsd = p.res ? p.res + pix * p.ldres + cbase : nullptr;
 #pragma unroll
-        for (int c0 = 0; c0 < NC; c0 += 32) {
-            float v[32];
-            tmem_ld32(tlane + (uint32_t)(2 * TN + c0), v);
-            tmem_ld_wait();
+                for (int c4 = 0; c4 < NC / 4; ++c4) {
+                    const int co = cbase + c4 * 4;
+                    if (co < p.Cout) {
+                        float o[4];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
-        }
-        const int m = q * 32 + lane;
-        const int ty = m >> p.tw_log2, tx = m & tw_mask;
-        const int ho = ho0 + ty, wo = wo0 + tx;
-        if (ho < p.Ho && wo < p.Wo) {
-            const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;
-            const int cbase = n0 + half * NC;
-            float* dst = p.y + pix * p.ldy + cbase;
-            const float* rsd = p.res ? p.res + pix * p.ldres + cbase : nullptr;
-#pragma unroll
-            for (int c4 = 0; c4 < NC / 4; ++c4) {
-                const int co = cbase + c4 * 4;
-                if (co < p.Cout) {
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        o[e] = acc[c4 * 4 + e];
-                        if (co + e < p.Cout) {
-                            if (p.bias) o[e] += __ldg(p.bias + co + e);
-                            if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
-                            if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                        for (int e = 0; e < 4; ++e) {
+                            o[e] = acc[c4 * 4 + e];
+                            if (co + e < p.Cout) {
+                                if (p.bias) o[e] += __ldg(p.bias + co + e);
+                                if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
+                                if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                            }
                         }
-                    }
-                    if (p.vec_out && co + 3 < p.Cout) {
-                        *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    } else {
+                        if (p.vec_out && co + 3 < p.Cout) {
+                            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (co + e < p.Cout) dst[c4 * 4 + e] = o[e];
+                            for (int e = 0; e < 4; ++e)
+                                if (co + e < p.Cout) dst[c4 * 4 + e] = o[e];
+                        }
                     }
                 }
             }
         }
     } else if (warp == 12) {
         if (lane == 0) {
-            // ===== activation TMA producer =====
+            // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
             uint32_t pr = 0;
-            int tap = 0, cc = 0;
-            const int wbase = wo0 * p.stride - p.pad, hbase = ho0 * p.stride - p.pad;
-            for (int it = 0; it < nIt; ++it) {
-                mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
-                mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
-                const int r = tap / p.kw, s = tap - r * p.kw;
-                tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, cc * C2_KC, wbase + s * p.dil, hbase + r * p.dil, n,
-                            RAW_FULL(sr));
-                if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
-                if (++cc == p.ncc) { cc = 0; ++tap; }
+            const int nrc = (p.ncc + 1) >> 1;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const Tile tl = decode(t);
+                const int wbase = tl.wo0 * p.stride - p.pad, hbase = tl.ho0 * p.stride - p.pad;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const int r = tap / p.kw, s = tap - r * p.kw;
+                    for (int rc = 0; rc < nrc; ++rc) {
+                        mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
+                        mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
+                        tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil,
+                                    hbase + r * p.dil, tl.n, RAW_FULL(sr));
+                        if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp == 13) {
         if (lane == 0) {
             // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
-            int so = 0;
-            uint32_t po = 0;
-            const int rb = n0 / C2_WRB;
-            const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
-            for (int it = 0; it < nIt; ++it) {
-                mbar_wait(OP_EMPTY(so), po ^ 1u);
-                mbar_arrive_expect_tx(OP_FULL(so), Cfg::B_BYTES);
-                const uint32_t sb = op0 + so * Cfg::OP_BYTES + Cfg::A_SMEM;
-                const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
-                if (TN == C2_WRB) {
-                    bulk_g2s(sb, src, C2_WCHUNK, OP_FULL(so));
-                } else {
-                    const uint32_t sub = (uint32_t)(n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
+            int sb_ = 0;
+            uint32_t pb = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const Tile tl = decode(t);
+                const int rb = tl.n0 / C2_WRB;
+                const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
+                const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
+                for (int it = 0; it < nIt; ++it) {
+                    mbar_wait(B_EMPTY(sb_), pb ^ 1u);
+                    mbar_arrive_expect_tx(B_FULL(sb_), Cfg::B_BYTES);
+                    const uint32_t sb = op0 + sb_ * Cfg::B_BYTES;
+                    const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
+                    if (TN == C2_WRB) {
+                        bulk_g2s(sb, src, C2_WCHUNK, B_FULL(sb_));
+                    } else {
 #pragma unroll
-                    for (int blk = 0; blk < 4; ++blk)
-                        bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, OP_FULL(so));
+                        for (int blk = 0; blk < 4; ++blk)
+                            bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, B_FULL(sb_));
+                    }
+                    if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
                 }
-                if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
     } else if (warp == 14) {
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
         const uint32_t idesc = idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t d_corr = tb + 2 * TN;
-        int so = 0, b = 0, in_chunk = 0;
-        uint32_t po = 0, pe0 = 0, pe1 = 0;
-        for (int it = 0; it < nIt; ++it) {
-            mbar_wait(OP_FULL(so), po);
-            if (in_chunk == 0) {
-                if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
-                else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
-            }
-            tc_fence_after();
-            const bool last = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
-            if (elect_one()) {
-                const uint32_t sa = op0 + so * Cfg::OP_BYTES;
-                const uint32_t sb = sa + Cfg::A_SMEM;
-                const uint32_t d_main = tb + (uint32_t)(b * TN);
+        int so = 0, sbi = 0, b = 0, cb = 0;
+        uint32_t po = 0, pb = 0, pe0 = 0, pe1 = 0, pc0 = 0, pc1 = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const uint32_t d_corr = tb + (uint32_t)((2 + cb) * TN);
+            // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
+            if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
+            else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
+            int in_chunk = 0;
+            for (int it = 0; it < nIt; ++it) {
+                mbar_wait(B_FULL(sbi), pb);
+                mbar_wait(OP_FULL(so), po);
+                if (in_chunk == 0) {
+                    if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
+                    else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
+                }
+                tc_fence_after();
+                const bool last = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
+                if (elect_one()) {
+                    const uint32_t sb = op0 + sbi * Cfg::B_BYTES;
+                    const uint32_t d_main = tb + (uint32_t)(b * TN);
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
-                    const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
-                    const uint32_t acc_main = (in_chunk > 0 || ks > 0) ? 1u : 0u, acc_corr = (it > 0 || ks > 0) ? 1u : 0u;
-                    if (TS) {
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
+                        const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
+                        const uint32_t acc_main = (in_chunk > 0 || ks > 0) ? 1u : 0u, acc_corr = (it > 0 || ks > 0) ? 1u : 0u;
                         const uint32_t ta_hi = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32 + ks * 16), ta_lo = ta_hi + 8;
                         mma_tf32_ts(d_main, ta_hi, dbh, idesc, acc_main);
                         mma_tf32_ts(d_corr, ta_lo, dbh, idesc, acc_corr);
                         mma_tf32_ts(d_corr, ta_hi, dbl, idesc, 1u);
-                    } else {
-                        const uint32_t a_hi = sa + ks * C2_RAW_BYTES, a_lo = a_hi + C2_RAW_BYTES / 2;
-                        const uint64_t dah = smem_desc(a_hi, LBO_BYTES, SBO_BYTES), dal = smem_desc(a_lo, LBO_BYTES, SBO_BYTES);
-                        mma_tf32(d_main, dah, dbh, idesc, acc_main);
-                        mma_tf32(d_corr, dal, dbh, idesc, acc_corr);
-                        mma_tf32(d_corr, dah, dbl, idesc, 1u);
                     }
+                    mma_commit(OP_EMPTY(so));
+                    mma_commit(B_EMPTY(sbi));
+                    if (last) mma_commit(MAIN_FULL(b));
                 }
-                mma_commit(OP_EMPTY(so));
-                if (last) mma_commit(MAIN_FULL(b));
+                __syncwarp();
+                if (last) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
+                if (++so == C2_NO) { so = 0; po ^= 1u; }
+                if (++sbi == C2_NB) { sbi = 0; pb ^= 1u; }
             }
-            __syncwarp();
-            if (last) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
-            if (++so == C2_NO) { so = 0; po ^= 1u; }
+            if (NCB == 2) cb ^= 1;
         }
     }
     tc_fence_before();
@@ -466,19 +453,29 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int TN, bool TS>
+template <int TN>
 static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv2_kernel<TN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, TS>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
         attr = true;
     }
-    dim3 grid(tiles, cdiv(p.Cout, TN));
-    conv2_kernel<TN, TS><<<grid, C2_THREADS, C2Cfg<TN, TS>::SMEM, stream>>>(map, p);
+    Conv2P q = p;
+    q.tiles_n = cdiv(p.Cout, TN);
+    q.total_tiles = tiles * q.tiles_n;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int grid = q.total_tiles < sms ? q.total_tiles : sms;      // persistent: one CTA per SM walks the tile list
+    conv2_kernel<TN><<<grid, C2_THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
     return launch_status("aoc_conv2d_nhwc_tc");
 }
 
-int g_conv_ts = 1;      // aoc_set_option("conv_ts", 0/1)
+int g_conv_chunk = 8;   // aoc_set_option("conv_chunk", stages): default accumulation chain length
 
 }  // namespace aoc
 
@@ -525,7 +522,8 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.dil = dil; p.relu = relu; p.in_relu = in_relu;
     p.ncc = cdiv(Cin, C2_KC);
     p.nIt = kh * kw * p.ncc;
-    p.chunk = chunk_stages > 0 ? chunk_stages : 8;
+    p.chunk = chunk_stages > 0 ? chunk_stages : g_conv_chunk;
+    p.taps = kh * kw;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     // pixel-patch geometry: 1x1/s1/p0 convolutions see each image as one row of H*W pixels
     int gW = W, gH = H;
@@ -546,10 +544,10 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     CUtensorMap map;
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)gW * ldx * 4, (cuuint64_t)gH * gW * ldx * 4};
-    cuuint32_t box[4] = {(cuuint32_t)C2_KC, (cuuint32_t)(tw * stride), (cuuint32_t)(p.th * stride), 1u};
+    cuuint32_t box[4] = {(cuuint32_t)C2_RKC, (cuuint32_t)(tw * stride), (cuuint32_t)(p.th * stride), 1u};
     cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
     CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         set_error("aoc_conv2d_nhwc_tc: cuTensorMapEncodeTiled failed (%d) dims %d x %d x %d x %d ld %d box %d x %d", (int)cr, Cin,
@@ -559,6 +557,5 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     const int tiles = N * p.tiles_x * p.tiles_y;
     // narrow N tile when the layer is too small to fill the chip with 128-wide tiles
     const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148;
-    if (g_conv_ts) return narrow ? launch_conv2<64, true>(map, p, tiles, stream) : launch_conv2<128, true>(map, p, tiles, stream);
-    return narrow ? launch_conv2<64, false>(map, p, tiles, stream) : launch_conv2<128, false>(map, p, tiles, stream);
+    return narrow ? launch_conv2<64>(map, p, tiles, stream) : launch_conv2<128>(map, p, tiles, stream);
 }

@@ -160,7 +160,6 @@ class Engine:
         self.tc_conv = tc and os.environ.get("AOCB200_TC_CONV", "1") != "0"
         self.tc_match = tc and os.environ.get("AOCB200_TC_MATCH", "1") != "0"
         self._wpacked = {}
-        self.L.set_option(b"conv_ts", 0 if os.environ.get("AOCB200_CONV_TS", "1") == "0" else 1)
         self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self.use_graphs = os.environ.get("AOCB200_GRAPHS", "1") != "0"

@@ -47,8 +47,8 @@ int aoc_version(void);
 const char* aoc_last_error_string(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
 int aoc_check_device(int dev);
-/* tuning / diagnostic switches.  "conv_ts" (default 1): the tensor-core convolution keeps its split activation operand
- * in tensor memory (1) or in shared memory (0); both give identical results. */
+/* tuning / diagnostic switches.  "conv_chunk" (default 8): default length, in 16-channel stages, of the TMEM
+ * accumulation chains of the tensor-core convolution (see aoc_conv2d_nhwc_tc). */
 int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */

@@ -9,6 +9,12 @@ from aocb200.engine import Engine, T  # noqa: E402
 from aocb200.params import synthetic_state_dict  # noqa: E402
 
 SHAPES = [
+    ("tiny 16->64 1x1 @31x54 (1 stage, 14 CTAs)", 1, 31, 54, 16, 64, 1, 1, 0, 1, False),
+    ("tiny 64->64 1x1 @31x54 (4 stages)", 1, 31, 54, 64, 64, 1, 1, 0, 1, False),
+    ("tiny 256->64 1x1 @31x54 (16 stages)", 1, 31, 54, 256, 64, 1, 1, 0, 1, False),
+    ("tiny 1024->64 1x1 @31x54 (64 stages)", 1, 31, 54, 1024, 64, 1, 1, 0, 1, False),
+    ("tiny 1024->128 1x1 @121x213 (64 stages, 202 CTAs)", 1, 121, 213, 1024, 128, 1, 1, 0, 1, False),
+
     # name, N, H, W, Cin, Cout, k, stride, pad, dil, affine
     ("dec.conv1 320->128 3x3 @121x213x6", 6, 121, 213, 320, 128, 3, 1, 1, 1, False),
     ("dec.conv2 128->128 3x3 @121x213x6", 6, 121, 213, 128, 128, 3, 1, 1, 1, False),
