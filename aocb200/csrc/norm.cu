@@ -163,6 +163,18 @@ __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// tile partials [N * tiles_per_image][2][C] floats (written by the convolution epilogue) -> stats [N][2][C] doubles
+__global__ void tile_stats_reduce_kernel(const float* __restrict__ part, int tiles_per_image, int C2,
+                                         double* __restrict__ stats) {
+    int n = blockIdx.y;
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C2) return;
+    double a = 0.0;
+    const float* p = part + (size_t)n * tiles_per_image * C2 + c;
+    for (int t = 0; t < tiles_per_image; ++t) a += (double)__ldg(p + (size_t)t * C2);
+    stats[(size_t)n * C2 + c] = a;
+}
+
 static int stats_slab(int HW) {
     int pb = 256;
     while ((long long)cdiv(HW, pb) > 1024) pb *= 2;
@@ -202,6 +214,14 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
     dim3 g2(cdiv(2 * C, 256), N);
     channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
     return launch_status("aoc_channel_stats_f32");
+}
+
+extern "C" int aoc_tile_stats_reduce_f32(const float* tile_stats, int N, int tiles_per_image, int C, double* stats,
+                                         cudaStream_t stream) {
+    AOC_CHECK_ARG(tile_stats && stats && N > 0 && tiles_per_image > 0 && C > 0, "bad args");
+    dim3 g(cdiv(2 * C, 128), N);
+    tile_stats_reduce_kernel<<<g, 128, 0, stream>>>(tile_stats, tiles_per_image, 2 * C, stats);
+    return launch_status("aoc_tile_stats_reduce_f32");
 }
 
 extern "C" int aoc_gn_coeffs_f32(const double* stats, const float* gamma, const float* beta, int N, int C, int groups,

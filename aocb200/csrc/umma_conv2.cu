@@ -45,6 +45,7 @@ constexpr int C2_THREADS = 512;
 
 struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
+    float* tile_stats;      // optional [pixel tiles][2][Cout]: per-tile sum / sum of squares of the stored output
     int N, H, W, Cin, Ho, Wo, Cout, ldy, ldres, kw, stride, pad, dil, relu, in_relu;
     int tw_log2, th, tiles_x, tiles_y;
     int ncc, nIt, chunk, taps;
@@ -60,6 +61,26 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// v[i] summed over the 32 lanes of the warp, result for index `lane` returned in every lane (transposing butterfly:
+// 31 shuffles instead of 32 x 5; fixed order -> deterministic)
+__device__ __forceinline__ float warp_transpose_sum32(const float* v, int lane) {
+    float a16[16], a8[8], a4[4], a2[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        a16[i] = (h16 ? v[i + 16] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 16], 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        a8[i] = (h8 ? a16[i + 8] : a16[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a16[i] : a16[i + 8], 8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        a4[i] = (h4 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h4 ? a8[i] : a8[i + 4], 4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        a2[i] = (h2 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h2 ? a4[i] : a4[i + 2], 2);
+    return (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
+}
+
 // Ring depths are sized for LATENCY, not bandwidth: a weight chunk is requested when the MMAs of the stage it replaces
 // retire and must have landed (L2 round trip ~1.5k cycles) before its own MMAs are due, so the weight ring is 8 stages
 // deep (with 4 the kernel ran at ~600 cycles per stage regardless of the tile width: 4 stages per round trip).
@@ -70,7 +91,8 @@ struct C2Cfg {
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + C2_NB * B_BYTES;
-    static constexpr uint32_t BAR_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;
+    static constexpr uint32_t STAT_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;    // [4 quadrants][2 stats][TN] floats
+    static constexpr uint32_t BAR_OFF = STAT_OFF + 4 * 2 * TN * 4;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr int NCB = TN <= 64 ? 2 : 1;             // CORR accumulators: double buffered across tiles when they fit
@@ -277,25 +299,29 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
             if (NCB == 2) cb ^= 1;
             const int ho = tl.ho0 + ty, wo = tl.wo0 + tx;
-            if (ho < p.Ho && wo < p.Wo) {
-                const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
-                const int cbase = tl.n0 + half * NC;
+            const bool valid = ho < p.Ho && wo < p.Wo;
+            const int cbase = tl.n0 + half * NC;
+            {
+                const size_t pix = valid ? ((size_t)tl.n * p.Ho + ho) * p.Wo + wo : 0;
                 float* dst = p.y + pix * p.ldy + cbase;
                 const float* rsd = p.res ? p.res + pix * p.ldres + cbase : nullptr;
 #pragma unroll
                 for (int c4 = 0; c4 < NC / 4; ++c4) {
                     const int co = cbase + c4 * 4;
-                    if (co < p.Cout) {
-                        float o[4];
+                    float o[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            o[e] = acc[c4 * 4 + e];
-                            if (co + e < p.Cout) {
-                                if (p.bias) o[e] += __ldg(p.bias + co + e);
-                                if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
-                                if (p.relu) o[e] = fmaxf(o[e], 0.f);
-                            }
+                    for (int e = 0; e < 4; ++e) {
+                        o[e] = acc[c4 * 4 + e];
+                        if (valid && co + e < p.Cout) {
+                            if (p.bias) o[e] += __ldg(p.bias + co + e);
+                            if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
+                            if (p.relu) o[e] = fmaxf(o[e], 0.f);
+                        } else {
+                            o[e] = 0.f;
                         }
+                        acc[c4 * 4 + e] = o[e];                 // final values (0 outside the image / beyond Cout)
+                    }
+                    if (valid && co < p.Cout) {
                         if (p.vec_out && co + 3 < p.Cout) {
                             *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
@@ -305,6 +331,30 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                         }
                     }
                 }
+            }
+            if (p.tile_stats) {
+                // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels
+                float* st = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);      // [q][stat][TN]
+#pragma unroll
+                for (int c0 = 0; c0 < NC; c0 += 32) {
+                    const float s1 = warp_transpose_sum32(acc + c0, lane);
+                    float sq[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) sq[e] = acc[c0 + e] * acc[c0 + e];
+                    const float s2 = warp_transpose_sum32(sq, lane);
+                    st[(q * 2 + 0) * TN + half * NC + c0 + lane] = s1;
+                    st[(q * 2 + 1) * TN + half * NC + c0 + lane] = s2;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const int i = threadIdx.x - 128;                                 // 0..255 over [stat][TN] (TN <= 128)
+                if (i < 2 * TN) {
+                    const int stat = i / TN, ch = i - stat * TN;
+                    const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
+                                      st[(2 * 2 + stat) * TN + ch]) + st[(3 * 2 + stat) * TN + ch];
+                    const int mt = t / p.tiles_n;
+                    if (tl.n0 + ch < p.Cout) p.tile_stats[((size_t)mt * 2 + stat) * p.Cout + tl.n0 + ch] = t4;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
     } else if (warp == 12) {
@@ -498,10 +548,35 @@ extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, i
     return launch_status("aoc_conv_pack_weights_tf32x3");
 }
 
+// pixel-patch geometry shared by the launcher and the tile-statistics consumers
+static void conv_geometry(int H, int W, int kh, int kw, int stride, int pad, int dil, int* gH, int* gW, int* Ho, int* Wo,
+                          int* tw_log2) {
+    *Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1;
+    *Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+    *gW = W; *gH = H;
+    // 1x1/s1/p0 convolutions see each image as one row of H*W pixels
+    if (kh == 1 && kw == 1 && stride == 1 && pad == 0) { *gW = H * W; *gH = 1; *Wo = *gW; *Ho = 1; }
+    int best_l2 = 7;
+    long long best_tiles = -1;
+    for (int l2 = 7; l2 >= 3; --l2) {
+        int tw = 1 << l2, th = C2_BM >> l2;
+        long long t = (long long)cdiv(*Wo, tw) * cdiv(*Ho, th);
+        if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_l2 = l2; }
+    }
+    *tw_log2 = best_l2;
+}
+
+extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride, int pad, int dil) {
+    int gH, gW, Ho, Wo, l2;
+    conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
+    if (Ho <= 0 || Wo <= 0) return 0;
+    return cdiv(Wo, 1 << l2) * cdiv(Ho, C2_BM >> l2);
+}
+
 extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
-                                  const float* in_a, const float* in_b, int in_relu, float* y, int N, int H, int W,
-                                  int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad,
-                                  int dil, int relu, int chunk_stages, cudaStream_t stream) {
+                                  const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N,
+                                  int H, int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw,
+                                  int stride, int pad, int dil, int relu, int chunk_stages, cudaStream_t stream) {
     AOC_CHECK_ARG(x && w_packed && y, "null pointer");
     AOC_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && dil > 0, "bad dims");
     AOC_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
@@ -513,11 +588,12 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
         set_error("aoc_conv2d_nhwc_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver)");
         return AOC_ELAUNCH;
     }
-    int Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1;
-    int Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+    int gH, gW, Ho, Wo, best_l2;
+    conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &best_l2);
     AOC_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
     Conv2P p;
     p.w = (const uint8_t*)w_packed; p.bias = bias; p.res = residual; p.in_a = in_a; p.in_b = in_b; p.y = y;
+    p.tile_stats = tile_stats;
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.ldy = ldy; p.ldres = ldres; p.kw = kw; p.stride = stride; p.pad = pad;
     p.dil = dil; p.relu = relu; p.in_relu = in_relu;
     p.ncc = cdiv(Cin, C2_KC);
@@ -525,16 +601,6 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.chunk = chunk_stages > 0 ? chunk_stages : g_conv_chunk;
     p.taps = kh * kw;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
-    // pixel-patch geometry: 1x1/s1/p0 convolutions see each image as one row of H*W pixels
-    int gW = W, gH = H;
-    if (kh == 1 && kw == 1 && stride == 1 && pad == 0) { gW = H * W; gH = 1; Wo = gW; Ho = 1; }
-    int best_l2 = 7;
-    long long best_tiles = -1;
-    for (int l2 = 7; l2 >= 3; --l2) {
-        int tw = 1 << l2, th = C2_BM >> l2;
-        long long t = (long long)cdiv(Wo, tw) * cdiv(Ho, th);
-        if (best_tiles < 0 || t < best_tiles) { best_tiles = t; best_l2 = l2; }
-    }
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
     p.tw_log2 = best_l2;
     p.th = C2_BM >> best_l2;

@@ -192,8 +192,9 @@ class Engine:
 
     # ------------------------------------------------------------------ layer helpers
     def conv(self, x, name, stride=1, pad=0, dil=1, relu=False, res=None, in_scale=None, out=None, in_shift=None,
-             in_relu=False):
-        """y = conv(relu?(x * in_scale[n,c] + in_shift[n,c])) + bias (+ res) (ReLU)"""
+             in_relu=False, stats=False):
+        """y = conv(relu?(x * in_scale[n,c] + in_shift[n,c])) + bias (+ res) (ReLU).  stats=True also returns the
+        per-(sample, channel) sum / sum of squares of y ([N][2][C] doubles), taken in the convolution epilogue."""
         w, b, (Cout, kh, kw, Cin) = self.w.conv[name]
         assert Cin == x.C, (name, Cin, x.C)
         Ho = (x.H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
@@ -208,16 +209,24 @@ class Engine:
                 self.L.conv_pack_weights_tf32x3(w.data_ptr(), Cout, Cin, kh, kw, buf.data_ptr(), self.stream)
                 wp = (w, buf)
                 self._wpacked[name] = wp
+            ts = None
+            if stats:
+                tpi = self.L.conv_tiles_per_image(x.H, x.W, kh, kw, stride, pad, dil)
+                ts = self.empty(x.N * tpi * 2 * Cout)
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
-                                  _p(in_shift), 1 if in_relu else 0, out.ptr, x.N, x.H, x.W, Cin, x.ld, Cout, out.ld,
-                                  0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
+                                  _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
+                                  out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
                                   self.conv_chunk, self.stream)
-            return out
+            if not stats:
+                return out
+            st = self.empty(x.N * 2 * Cout, torch.float64)
+            self.L.tile_stats_reduce_f32(ts.data_ptr(), x.N, tpi, Cout, st.data_ptr(), self.stream)
+            return out, st
         assert in_shift is None and not in_relu, "the fp32 SIMT convolution only fuses an input scale"
         self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
                                x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw, stride,
                                pad, dil, 1 if relu else 0, self.stream)
-        return out
+        return (out, self.stats(out)) if stats else out
 
     def stats(self, x, phi=None, thr=None):
         L = self.L
@@ -234,13 +243,18 @@ class Engine:
                              x.N, x.HW, x.C, x.ld, out.ld, 0 if res is None else res.ld, 1 if relu else 0, self.stream)
         return out
 
-    def gn(self, x, name, groups, relu=False, res=None, out=None):
-        st = self.stats(x)
+    def gn_ab(self, x, name, groups, st=None):
+        """nn.GroupNorm(groups, C) of x as per-(sample, channel) coefficients: y = x * a + b"""
+        st = self.stats(x) if st is None else st
         a, b = self.empty(x.N * x.C), self.empty(x.N * x.C)
         self.L.gn_coeffs_f32(st.data_ptr(), self.w.vec[name + ".weight"].data_ptr(),
                              self.w.vec[name + ".bias"].data_ptr(), x.N, x.C, groups, x.HW, 1e-5, a.data_ptr(),
                              b.data_ptr(), self.stream)
-        return self.affine(x, a, b, res=res, relu=relu, out=out)
+        return a, b
+
+    def gn(self, x, name, groups, relu=False, res=None, out=None, st=None, res_scale=None):
+        a, b = self.gn_ab(x, name, groups, st)
+        return self.affine(x, a, b, res=res, res_scale=res_scale, relu=relu, out=out)
 
     def gct_gate(self, x, name, st=None, pre=None):
         st = self.stats(x) if st is None else st
@@ -328,9 +342,14 @@ class Engine:
         z = self.new(1, y.H, y.W, 256)
         L.dwconv3x3_nhwc_f32(y.ptr, v["seperate_conv.weight"].data_ptr(), v["seperate_conv.bias"].data_ptr(), z.ptr, 1,
                              y.H, y.W, 256, self.stream)
-        z = self.gn(z, "bn1", 32, relu=True)
-        z = self.conv(z, "embedding_conv")
-        emb = self.gn(z, "bn2", 25, relu=True)
+        if self.tc_conv:
+            a1, b1 = self.gn_ab(z, "bn1", 32)
+            z, s2 = self.conv(z, "embedding_conv", in_scale=a1, in_shift=b1, in_relu=True, stats=True)
+            emb = self.gn(z, "bn2", 25, relu=True, st=s2)
+        else:
+            z = self.gn(z, "bn1", 32, relu=True)
+            z = self.conv(z, "embedding_conv")
+            emb = self.gn(z, "bn2", 25, relu=True)
         return emb, low
 
     # ------------------------------------------------------------------ matching (aocnet.py:128-358)
@@ -514,8 +533,8 @@ class Engine:
         L.prehead_assemble_f32(g.data_ptr(), gc.data_ptr(), gp.data_ptr(), loc.ptr, locp.ptr, ldl, prev_ids.data_ptr(),
                                hw, O, pre.ptr, st)
         x = self.new(O, h, w, EMB + 64)
-        t = self.conv(pre, "dynamic_prehead.conv")
-        self.gn(t, "dynamic_prehead.bn", 16, relu=True, out=x.slice(EMB, 64))
+        t, s_t = self.conv(pre, "dynamic_prehead.conv", stats=True)
+        self.gn(t, "dynamic_prehead.bn", 16, relu=True, out=x.slice(EMB, 64), st=s_t)
         L.broadcast_rows_f32(q.ptr, x.ptr, O, hw, EMB, q.ld, x.ld, st)
         if self.keep_debug:
             self.debug.update(g=g, gc=gc, gp=gp, loc=loc, locp=locp, pre=pre, head=head, P=P, pvalid=pvalid,
@@ -549,17 +568,33 @@ class Engine:
     def gn_bottleneck(self, x, p, stride=1, dil=1):
         """layers/gct.py:68-91"""
         gate = self.gct_gate(x, p + ".GCT1")
-        y = self.conv(x, p + ".conv1", in_scale=gate)
-        y = self.gn(y, p + ".bn1", 32, relu=True)
-        y = self.conv(y, p + ".conv2", stride=stride, pad=dil, dil=dil)
-        y = self.gn(y, p + ".bn2", 32, relu=True)
-        y = self.conv(y, p + ".conv3")
+        if not self.tc_conv:
+            y = self.conv(x, p + ".conv1", in_scale=gate)
+            y = self.gn(y, p + ".bn1", 32, relu=True)
+            y = self.conv(y, p + ".conv2", stride=stride, pad=dil, dil=dil)
+            y = self.gn(y, p + ".bn2", 32, relu=True)
+            y = self.conv(y, p + ".conv3")
+            if (p + ".downsample.0") in self.w.conv:
+                r = self.conv(x, p + ".downsample.0", stride=stride)
+                r = self.gn(r, p + ".downsample.1", 32)
+            else:
+                r = x
+            return self.gn(y, p + ".bn3", 32, relu=True, res=r)
+        # tensor-core path: GroupNorm statistics come out of each convolution's epilogue and the normalisation (+ReLU)
+        # is applied inside the NEXT convolution's operand path -- the normalised tensors bn1/bn2 never exist in HBM
+        y1, s1 = self.conv(x, p + ".conv1", in_scale=gate, stats=True)
+        a1, b1 = self.gn_ab(y1, p + ".bn1", 32, s1)
+        y2, s2 = self.conv(y1, p + ".conv2", stride=stride, pad=dil, dil=dil, in_scale=a1, in_shift=b1, in_relu=True,
+                           stats=True)
+        a2, b2 = self.gn_ab(y2, p + ".bn2", 32, s2)
+        y3, s3 = self.conv(y2, p + ".conv3", in_scale=a2, in_shift=b2, in_relu=True, stats=True)
+        a3, b3 = self.gn_ab(y3, p + ".bn3", 32, s3)
         if (p + ".downsample.0") in self.w.conv:
-            r = self.conv(x, p + ".downsample.0", stride=stride)
-            r = self.gn(r, p + ".downsample.1", 32)
-        else:
-            r = x
-        return self.gn(y, p + ".bn3", 32, relu=True, res=r)
+            r, sr = self.conv(x, p + ".downsample.0", stride=stride, stats=True)
+            ar, br = self.gn_ab(r, p + ".downsample.1", 32, sr)
+            # relu(GN3(y3) + GN_ds(r)) = relu(y3*a3 + (b3 + br) + r*ar)
+            return self.affine(y3, a3, b3 + br, res=r, res_scale=ar, relu=True)
+        return self.affine(y3, a3, b3, res=x, relu=True)
 
     def cond_block(self, x, p, beta=0.3):
         """conditioning_block / conditioning_layer (conditioning_layer.py:24-86) with CL_2/CL_3 folded"""
@@ -594,14 +629,14 @@ class Engine:
         for i, d in ((1, 0), (2, 6), (3, 12), (4, 18)):
             q = "%s.aspp%d" % (p, i)
             gate = self.gct_gate(x, q + ".GCT", st=st)
-            y = self.conv(x, q + ".atrous_conv", pad=d, dil=max(d, 1), in_scale=gate)
-            self.gn(y, q + ".bn", 32, relu=True, out=cat.slice(128 * (i - 1), 128))
+            y, s_y = self.conv(x, q + ".atrous_conv", pad=d, dil=max(d, 1), in_scale=gate, stats=True)
+            self.gn(y, q + ".bn", 32, relu=True, out=cat.slice(128 * (i - 1), 128), st=s_y)
         g = T(self.gap(x, st), O, 1, 1, x.C)
         g = self.conv(g, p + ".global_avg_pool.1", relu=True)
         self.resize_bilinear(g, x.H, x.W, out=cat.slice(512, 128))
         gate = self.gct_gate(cat, p + ".GCT")
-        y = self.conv(cat, p + ".conv1", in_scale=gate)
-        return self.gn(y, p + ".bn1", 32, relu=True)
+        y, s_y = self.conv(cat, p + ".conv1", in_scale=gate, stats=True)
+        return self.gn(y, p + ".bn1", 32, relu=True, st=s_y)
 
     def modulator(self, x, mem, head, p, tag):
         """decoding_module.py:192-210"""
@@ -655,15 +690,17 @@ class Engine:
         xu = cat.slice(256, 256)
         L.resize_bicubic_nhwc_f32(x.ptr, xu.ptr, O, x.H, x.W, h, w, 256, x.ld, 512, self.stream)
         gate = self.gct_gate(cat, p + ".GCT_sc")
-        sc = self.conv(cat, p + ".conv_sc", in_scale=gate)
+        sc, s_sc = self.conv(cat, p + ".conv_sc", in_scale=gate, stats=True)
         cat2 = self.new(O, h, w, 320)                      # [x (256) | sc (64)]
         self.copy_channels(xu, cat2.slice(0, 256))
-        self.gn(sc, p + ".bn_sc", 16, relu=True, out=cat2.slice(256, 64))
+        self.gn(sc, p + ".bn_sc", 16, relu=True, out=cat2.slice(256, 64), st=s_sc)
         x = cat2
         x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA10")
-        x = self.gn(self.conv(x, p + ".conv1", pad=1), p + ".bn1", 32, relu=True)
+        y, s_y = self.conv(x, p + ".conv1", pad=1, stats=True)
+        x = self.gn(y, p + ".bn1", 32, relu=True, st=s_y)
         x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA11")
-        x = self.gn(self.conv(x, p + ".conv2", pad=1), p + ".bn2", 32, relu=True)
+        y, s_y = self.conv(x, p + ".conv2", pad=1, stats=True)
+        x = self.gn(y, p + ".bn2", 32, relu=True, st=s_y)
         wfg = self.linear(head, p + ".IA_final_fg", O)
         wbg = self.linear(head, p + ".IA_final_bg", O)
         fg, bg, logits = self.empty(O * h * w), self.empty(O * h * w), self.empty(O * h * w)

@@ -70,9 +70,16 @@ size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
 int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
                                  cudaStream_t stream);
 int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
-                       const float* in_a, const float* in_b, int in_relu, float* y, int N, int H, int W, int Cin,
-                       int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad, int dil, int relu,
-                       int chunk_stages, cudaStream_t stream);
+                       const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N, int H,
+                       int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad,
+                       int dil, int relu, int chunk_stages, cudaStream_t stream);
+/* tile_stats (optional): [N * aoc_conv_tiles_per_image(...)][2][Cout] floats receiving, per 128-pixel output tile, the
+ * per-channel sum and sum of squares of the stored output -- the GroupNorm / GCT statistics of the next layer come
+ * out of the convolution epilogue instead of a second pass over the tensor (aoc_tile_stats_reduce_f32 folds them into
+ * the [N][2][C] double layout of aoc_channel_stats_f32). */
+int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride, int pad, int dil);
+int aoc_tile_stats_reduce_f32(const float* tile_stats, int N, int tiles_per_image, int C, double* stats,
+                              cudaStream_t stream);
 /* depthwise 3x3 pad 1 + bias (aocnet.py:19 seperate_conv); w [C][3][3] */
 int aoc_dwconv3x3_nhwc_f32(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int C,
                            cudaStream_t stream);
