@@ -36,12 +36,12 @@ constexpr int C2_BM = 128;
 constexpr int C2_KC = 16;                               // input channels per operand stage (2 k-steps of 8)
 constexpr int C2_RKC = 32;                              // input channels per TMA box (128-byte rows)
 constexpr int C2_NO = 4;                                // activation operand ring depth (TMEM, 32 columns per stage)
-constexpr int C2_NB = 8;                                // weight ring depth (shared memory)
+constexpr int C2_NB = C2_NO;                            // weight ring: same stages as the activation operand ring
 constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_RKC * 4;   // 16384
 constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
 constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
 constexpr int C2_MAX_AFFINE_C = 1024;
-constexpr int C2_THREADS = 512;
+constexpr int C2_THREADS = 640;                         // 8 transform + 8 drain + 2 producer + 2 issuer warps
 
 struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
@@ -50,8 +50,11 @@ struct Conv2P {
     int tw_log2, th, tiles_x, tiles_y;
     int ncc, nIt, chunk, taps;
     int tiles_n, total_tiles;
+    unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event][stage < 256]
     int vec_out;
 };
+
+#define C2_TRACE(ev, st) do { if (p.trace && blockIdx.x == 0 && (st) < 256) p.trace[(ev) * 256 + (st)] = clock64(); } while (0)
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
@@ -81,12 +84,14 @@ __device__ __forceinline__ float warp_transpose_sum32(const float* v, int lane) 
     return (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
 }
 
-// Ring depths are sized for LATENCY, not bandwidth: a weight chunk is requested when the MMAs of the stage it replaces
-// retire and must have landed (L2 round trip ~1.5k cycles) before its own MMAs are due, so the weight ring is 8 stages
-// deep (with 4 the kernel ran at ~600 cycles per stage regardless of the tile width: 4 stages per round trip).
+// What bounds a stage (clock64 trace of the roles, tools/conv_trace.py): ONE thread issuing 6 tcgen05.mma + 2-3
+// tcgen05.commit per stage needs ~45 cycles per instruction, i.e. 400-550 cycles per stage against 384 (TN=128) / 192
+// (TN=64) cycles of tensor work, and the queue behind it is shallow, so the pipe idles during the loop overhead.  The
+// issue work is therefore split over TWO warps -- one feeds the MAIN accumulator (2 MMAs per stage), one the CORR
+// accumulator (4 MMAs per stage) -- and a stage's operands are released by one shared barrier (2 commits).
 template <int TN>
 struct C2Cfg {
-    static constexpr int NR = TN <= 64 ? 8 : 4;              // raw activation ring depth (128 pixels x 32 channels each)
+    static constexpr int NR = TN <= 64 ? 8 : 6;              // raw activation ring depth (128 pixels x 32 channels each)
     static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
@@ -114,9 +119,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
     auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
     auto RAW_EMPTY = [&](int s) { return bar0 + 8u * (C2_NR + s); };
     auto OP_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + s); };                       // activation operand (TMEM)
-    auto OP_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + C2_NO + s); };
+    auto OP_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + C2_NO + s); };              // both operands of a stage
     auto B_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + s); };            // weight operand (smem)
-    auto B_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + C2_NB + s); };
+    auto CORR_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + C2_NB + s); };
     auto MAIN_FULL = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + b); };
     auto MAIN_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + 2 + b); };
     auto CORR_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + 4 + b); };
@@ -144,14 +149,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
         return tl;
     };
 
-    if (warp == 15 && lane == 0) {
-        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
-        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1); }
-        for (int s = 0; s < C2_NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); }
+    if (warp == 17 && lane == 0) {
+        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 8); }
+        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 2); mbar_init(B_FULL(s), 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), 1);
+        }
         fence_barrier_init();
     }
-    if (warp == 14) {
+    if (warp == 18) {
         tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
         tmem_relinquish();
     }
@@ -160,109 +166,112 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ===== transform warps: thread <-> pixel row <-> TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
-        const int pp = threadIdx.x;
+    if (warp < 8) {
+        // ===== transform warps: two sets of four (set g owns the operand stages with an even / odd running index, so a
+        // set's per-stage instruction stream -- ~550 cycles -- has two stage-times to complete); thread <-> pixel row <->
+        // TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
+        const int g = warp >> 2;
+        const int pp = (warp & 3) * 32 + lane;
         const int ty = pp >> p.tw_log2, tx = pp & tw_mask;
         const uint32_t src_row = (uint32_t)(pp * 128);
         const uint32_t sw = (uint32_t)(pp & 7);                              // TMA SWIZZLE_128B: 16 B chunk ^= row % 8
-        const uint32_t a_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + Cfg::A_TMEM_COL;
+        const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_TMEM_COL;
         const bool need_mask = p.in_b != nullptr;
         int sr = 0, so = 0;
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
-        float v[16];
-        // channel chunk cc_ of a tap lives in raw stage sr, half cc_ & 1 (a fresh stage is awaited on even chunks)
-        auto load_raw = [&](int cc_) {
-            if ((cc_ & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
-            const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
-            const uint32_t c8 = (uint32_t)(cc_ & 1) * 4u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
-                             : "r"(rawb + (((c8 + j) ^ sw) << 4)));
-        };
-        bool primed = false;
+        int gi = 0;                                                          // running operand-stage index (parity = owner)
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const Tile tl = decode(t);
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
             if (affine && tl.n != tab_n) {
                 // per-(sample, channel) coefficient table of this image; only the transform warps touch it
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int cpad = p.ncc * C2_KC;
-                for (int c = pp; c < cpad; c += 128) {
+                for (int c = threadIdx.x; c < cpad; c += 256) {
                     const bool ok = c < p.Cin;
                     tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)tl.n * p.Cin + c) : 1.f) : 0.f;
                     tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)tl.n * p.Cin + c) : 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 tab_n = tl.n;
             }
-            if (!primed) { load_raw(0); primed = true; }
-            const bool more_tiles = t + (int)gridDim.x < p.total_tiles;
             int tap = 0, cc = 0;
-            for (int it = 0; it < nIt; ++it) {
-                if (affine) {
-                    bool ok = true;
-                    if (need_mask) {
-                        const int r = tap / p.kw, s = tap - r * p.kw;
-                        ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s * p.dil) < (unsigned)p.W;
-                    }
+            for (int it = 0; it < nIt; ++it, ++gi) {
+                // both sets walk every raw stage (so neither can lap the producer); only the owner reads its half
+                if ((cc & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
+                if ((gi & 1) == g) {
+                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(1, it);
+                    float v[16];
+                    const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
+                    const uint32_t c8 = (uint32_t)(cc & 1) * 4u;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
-                        const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
-                        v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
-                        v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
-                    }
-                    if (p.in_relu) {
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                                     : "r"(rawb + (((c8 + j) ^ sw) << 4)));
+                    if (affine) {
+                        bool ok = true;
+                        if (need_mask) {
+                            const int r = tap / p.kw, s_ = tap - r * p.kw;
+                            ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s_ * p.dil) < (unsigned)p.W;
+                        }
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-                    }
-                    if (!ok) {
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
+                            const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
+                            v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
+                            v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
+                        }
+                        if (p.in_relu) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = 0.f;
-                    }
-                }
-                // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
-                float o[32];
+                            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        if (!ok) {
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float h, l;
-                    split_tf32(v[e], h, l);
-                    o[(e >> 3) * 16 + (e & 7)] = h;
-                    o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                        }
+                    }
+                    // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
+                    float o[32];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float h, l;
+                        split_tf32(v[e], h, l);
+                        o[(e >> 3) * 16 + (e & 7)] = h;
+                        o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                    }
+                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(2, it);
+                    mbar_wait(OP_EMPTY(so), po ^ 1u);
+                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, it);
+                    tc_fence_after();
+                    tmem_st32(a_lane + (uint32_t)(so * 32), o);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(OP_FULL(so));
+                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, it);
                 }
                 __syncwarp();
-                if ((cc & 1) || cc == p.ncc - 1) {              // second half (or an odd tail) read: raw stage is free
+                if ((cc & 1) || cc == p.ncc - 1) {              // second half (or an odd tail) passed: raw stage is free
                     if (lane == 0) mbar_arrive(RAW_EMPTY(sr));
                     if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                 }
                 if (++cc == p.ncc) { cc = 0; ++tap; }
-                // the next stage's loads fly while this one is stored (the first stage of the next tile included)
-                if (it + 1 < nIt || more_tiles) load_raw(it + 1 < nIt ? cc : 0);
-                mbar_wait(OP_EMPTY(so), po ^ 1u);
-                tc_fence_after();
-                tmem_st32(a_lane + (uint32_t)(so * 32), o);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(OP_FULL(so));
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
-    } else if (warp < 12) {
+    } else if (warp < 16) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
         constexpr int NC = TN / 2;
-        const int dwp = warp - 4;
+        const int dwp = warp - 8;
         const int q = dwp & 3, half = dwp >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
         const int nchunks = (nIt + p.chunk - 1) / p.chunk;
         const int m = q * 32 + lane;
         const int ty = m >> p.tw_log2, tx = m & tw_mask;
         int b = 0, cb = 0;
-        uint32_t ph0 = 0u, ph1 = 0u;
+        uint32_t ph0 = 0u, ph1 = 0u, pcf0 = 0u, pcf1 = 0u;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const Tile tl = decode(t);
             float acc[NC];
@@ -285,7 +294,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
                 b ^= 1;
             }
-            // all MMAs of the tile (including CORR) are complete once its last MAIN_FULL has fired
+            // the correction terms are issued by their own warp: wait for its end-of-tile commit
+            if (cb == 0) { mbar_wait(CORR_FULL(0), pcf0); pcf0 ^= 1u; }
+            else         { mbar_wait(CORR_FULL(1), pcf1); pcf1 ^= 1u; }
+            tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < NC; c0 += 32) {
                 float v[32];
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                     st[(q * 2 + 1) * TN + half * NC + c0 + lane] = s2;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                const int i = threadIdx.x - 128;                                 // 0..255 over [stat][TN] (TN <= 128)
+                const int i = threadIdx.x - 256;                                 // 0..255 over [stat][TN] (TN <= 128)
                 if (i < 2 * TN) {
                     const int stat = i / TN, ch = i - stat * TN;
                     const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
@@ -357,7 +369,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
-    } else if (warp == 12) {
+    } else if (warp == 16) {
         if (lane == 0) {
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                     const int r = tap / p.kw, s = tap - r * p.kw;
                     for (int rc = 0; rc < nrc; ++rc) {
                         mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
+                        C2_TRACE(0, 2 * (tap * nrc + rc));
                         mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
                         tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil,
                                     hbase + r * p.dil, tl.n, RAW_FULL(sr));
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 13) {
+    } else if (warp == 17) {
         if (lane == 0) {
             // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
             int sb_ = 0;
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
                 for (int it = 0; it < nIt; ++it) {
-                    mbar_wait(B_EMPTY(sb_), pb ^ 1u);
+                    mbar_wait(OP_EMPTY(sb_), pb ^ 1u);
                     mbar_arrive_expect_tx(B_FULL(sb_), Cfg::B_BYTES);
                     const uint32_t sb = op0 + sb_ * Cfg::B_BYTES;
                     const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
@@ -404,21 +417,19 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 }
             }
         }
-    } else if (warp == 14) {
-        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop, one elected lane issues =====
+    } else if (warp == 18) {
+        // ===== MAIN issuer (hi*hi): the whole warp runs the (warp-uniform) loop, one elected lane issues =====
         const uint32_t idesc = idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-        int so = 0, sbi = 0, b = 0, cb = 0;
-        uint32_t po = 0, pb = 0, pe0 = 0, pe1 = 0, pc0 = 0, pc1 = 0;
+        int so = 0, b = 0;
+        uint32_t po = 0, pe0 = 0, pe1 = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const uint32_t d_corr = tb + (uint32_t)((2 + cb) * TN);
-            // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
-            if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
-            else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
             int in_chunk = 0;
             for (int it = 0; it < nIt; ++it) {
-                mbar_wait(B_FULL(sbi), pb);
+                mbar_wait(B_FULL(so), po);
+                if (lane == 0) C2_TRACE(5, it);
                 mbar_wait(OP_FULL(so), po);
+                if (lane == 0) C2_TRACE(6, it);
                 if (in_chunk == 0) {
                     if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
                     else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
@@ -426,33 +437,57 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 tc_fence_after();
                 const bool last = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
                 if (elect_one()) {
-                    const uint32_t sb = op0 + sbi * Cfg::B_BYTES;
+                    const uint32_t sb = op0 + so * Cfg::B_BYTES;
                     const uint32_t d_main = tb + (uint32_t)(b * TN);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
-                        const uint64_t dbh = smem_desc(b_hi, LBO_BYTES, SBO_BYTES), dbl = smem_desc(b_lo, LBO_BYTES, SBO_BYTES);
-                        const uint32_t acc_main = (in_chunk > 0 || ks > 0) ? 1u : 0u, acc_corr = (it > 0 || ks > 0) ? 1u : 0u;
-                        const uint32_t ta_hi = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32 + ks * 16), ta_lo = ta_hi + 8;
-                        mma_tf32_ts(d_main, ta_hi, dbh, idesc, acc_main);
-                        mma_tf32_ts(d_corr, ta_lo, dbh, idesc, acc_corr);
-                        mma_tf32_ts(d_corr, ta_hi, dbl, idesc, 1u);
-                    }
+                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32);
+                    mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
                     mma_commit(OP_EMPTY(so));
-                    mma_commit(B_EMPTY(sbi));
                     if (last) mma_commit(MAIN_FULL(b));
                 }
                 __syncwarp();
+                if (lane == 0) C2_TRACE(7, it);
                 if (last) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
-                if (++sbi == C2_NB) { sbi = 0; pb ^= 1u; }
+            }
+        }
+    } else if (warp == 19) {
+        // ===== CORR issuer (lo*hi + hi*lo), same structure =====
+        const uint32_t idesc = idesc_tf32(C2_BM, TN);
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int so = 0, cb = 0;
+        uint32_t po = 0, pc0 = 0, pc1 = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const uint32_t d_corr = tb + (uint32_t)((2 + cb) * TN);
+            // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
+            if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
+            else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
+            for (int it = 0; it < nIt; ++it) {
+                mbar_wait(B_FULL(so), po);
+                mbar_wait(OP_FULL(so), po);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sb = op0 + so * Cfg::B_BYTES;
+                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
+                        const uint32_t ta_hi = ta + (uint32_t)(ks * 16), ta_lo = ta_hi + 8;
+                        mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                    }
+                    mma_commit(OP_EMPTY(so));
+                    if (it == nIt - 1) mma_commit(CORR_FULL(cb));
+                }
+                __syncwarp();
+                if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
             if (NCB == 2) cb ^= 1;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 14) {
+    if (warp == 18) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -526,6 +561,7 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cuda
 }
 
 int g_conv_chunk = 8;   // aoc_set_option("conv_chunk", stages): default accumulation chain length
+unsigned long long* g_conv_trace = nullptr;
 
 }  // namespace aoc
 
@@ -566,6 +602,11 @@ static void conv_geometry(int H, int W, int kh, int kw, int stride, int pad, int
     *tw_log2 = best_l2;
 }
 
+extern "C" int aoc_conv_trace(void* device_buffer_8x256_u64) {
+    g_conv_trace = (unsigned long long*)device_buffer_8x256_u64;
+    return AOC_OK;
+}
+
 extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride, int pad, int dil) {
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
@@ -600,6 +641,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.nIt = kh * kw * p.ncc;
     p.chunk = chunk_stages > 0 ? chunk_stages : g_conv_chunk;
     p.taps = kh * kw;
+    p.trace = g_conv_trace;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
     p.tw_log2 = best_l2;
@@ -621,7 +663,8 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
         return AOC_EINVAL;
     }
     const int tiles = N * p.tiles_x * p.tiles_y;
-    // narrow N tile when the layer is too small to fill the chip with 128-wide tiles
-    const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148;
+    // narrow N tile when the layer is too small to fill the chip with 128-wide tiles, or when K is so short that the
+    // tile time is its epilogue (the 128-wide epilogue holds 64 accumulators per thread and runs out of registers)
+    const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148 || p.nIt < 32;
     return narrow ? launch_conv2<64>(map, p, tiles, stream) : launch_conv2<128>(map, p, tiles, stream);
 }

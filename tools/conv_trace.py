@@ -1,0 +1,40 @@
+"""Per-stage pipeline timeline of the tensor-core convolution (CTA 0): where do the cycles of a K-loop stage go?"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from aocb200.engine import Engine, T  # noqa: E402
+from aocb200.params import synthetic_state_dict  # noqa: E402
+
+EV = ["tma_issue(raw)", "raw_seen", "alu_done", "op_empty_seen", "published", "mma:b_full", "mma:op_full", "mma:issued"]
+
+
+def main():
+    dev = torch.device("cuda:0")
+    eng = Engine(synthetic_state_dict(1234), dev)
+    g = torch.Generator().manual_seed(0)
+    for name, N, H, W, Cin, Cout, k, pad in (("bb.layer3 256->256 3x3 @31x54", 1, 31, 54, 256, 256, 3, 1),
+                                             ("dec.conv1 320->128 3x3 @121x213x6", 6, 121, 213, 320, 128, 3, 1)):
+        x = T(torch.randn(N * H * W * Cin, generator=g).to(dev), N, H, W, Cin)
+        w = (torch.randn(Cout, k, k, Cin, generator=g) / (Cin * k * k) ** 0.5).to(dev)
+        eng.w.conv[name] = (w, None, (Cout, k, k, Cin))
+        out = eng.conv(x, name, pad=pad)
+        buf = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
+        eng.L.conv_trace(buf.data_ptr())
+        eng.conv(x, name, pad=pad, out=out)
+        torch.cuda.synchronize()
+        eng.L.conv_trace(None)
+        tr = buf.cpu().view(8, 256)
+        t0 = int(tr[0, 0])
+        print(name)
+        print("stage " + " ".join("%15s" % e for e in EV))
+        for s in list(range(0, 24)) + list(range(100, 112)):
+            print("%5d " % s + " ".join("%15d" % (int(tr[e, s]) - t0 if int(tr[e, s]) else -1) for e in range(8)))
+        d = (tr[7, 120] - tr[7, 40]).item() / 80.0
+        print("steady state: %.0f cycles per stage (MMA issue to MMA issue, stages 40..120)" % d)
+
+
+if __name__ == "__main__":
+    main()
