@@ -35,13 +35,11 @@ using namespace umma;
 constexpr int C2_BM = 128;
 constexpr int C2_KC = 16;                               // input channels per operand stage (2 k-steps of 8)
 constexpr int C2_RKC = 32;                              // input channels per TMA box (128-byte rows)
-constexpr int C2_NO = 4;                                // activation operand ring depth (TMEM, 32 columns per stage)
-constexpr int C2_NB = C2_NO;                            // weight ring: same stages as the activation operand ring
 constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_RKC * 4;   // 16384
 constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
 constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
 constexpr int C2_MAX_AFFINE_C = 1024;
-constexpr int C2_THREADS = 640;                         // 8 transform + 8 drain + 2 producer + 2 issuer warps
+constexpr int C2_THREADS = 672;                         // 8 transform + 8 drain + 2 producer + up to 3 issuer warps
 
 struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
@@ -92,23 +90,34 @@ __device__ __forceinline__ float warp_transpose_sum32(const float* v, int lane) 
 template <int TN>
 struct C2Cfg {
     static constexpr int NR = TN <= 64 ? 8 : 6;              // raw activation ring depth (128 pixels x 32 channels each)
+    // operand ring (activation half in TMEM, 32 columns per stage; weight half in shared memory): a weight chunk is
+    // requested when the stage it replaces retires and needs an L2 round trip (~1.5k cycles) to land, so the period of
+    // a stage cannot drop below (round trip + MMA time) / depth: 8 stages where TMEM has room (TN = 64), else 4
+    static constexpr int NO = TN <= 64 ? 8 : 4;
     static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
-    static constexpr uint32_t TAB_OFF = OP_OFF + C2_NB * B_BYTES;
+    static constexpr uint32_t TAB_OFF = OP_OFF + NO * B_BYTES;
     static constexpr uint32_t STAT_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;    // [4 quadrants][2 stats][TN] floats
     static constexpr uint32_t BAR_OFF = STAT_OFF + 4 * 2 * TN * 4;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr int NCB = TN <= 64 ? 2 : 1;             // CORR accumulators: double buffered across tiles when they fit
-    static constexpr uint32_t A_TMEM_COL = (2 + NCB) * TN;   // ring of C2_NO stages x 32 columns behind MAIN[2] + CORR[NCB]
+    // correction issuers: one warp for both terms (TN = 128, the tensor pipe is the limit), or one warp and one
+    // accumulator per term (TN = 64: a stage is only 192 tensor cycles, the ~75 cycles per tcgen05 instruction of an
+    // issuing thread are the limit -- so the 6 MMAs of a stage are spread over three threads)
+    static constexpr int NCI = 1;   // (a third issuer for TN = 64 was measured: no gain once the weight latency is the limit)
+    static constexpr int THREADS = (8 + 8 + 2 + 1 + NCI) * 32;
+    static constexpr uint32_t A_TMEM_COL = (2 + NCB * NCI) * TN;   // ring of C2_NO stages x 32 columns behind the accumulators
 };
 
 template <int TN>
-__global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
+__global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
     using Cfg = C2Cfg<TN>;
     constexpr int C2_NR = Cfg::NR;
+    constexpr int C2_NO = Cfg::NO, C2_NB = Cfg::NO;
     constexpr int NCB = Cfg::NCB;                            // CORR accumulator buffers (2 when TMEM allows)
+    constexpr int NCI = Cfg::NCI;                            // correction issuers / accumulators per buffer
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* tab_a = reinterpret_cast<float*>(smem + Cfg::TAB_OFF);
@@ -151,9 +160,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
 
     if (warp == 17 && lane == 0) {
         for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 8); }
-        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 2); mbar_init(B_FULL(s), 1); }
+        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1 + NCI); mbar_init(B_FULL(s), 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), 1);
+            mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), NCI);
         }
         fence_barrier_init();
     }
@@ -299,13 +308,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
             else         { mbar_wait(CORR_FULL(1), pcf1); pcf1 ^= 1u; }
             tc_fence_after();
 #pragma unroll
-            for (int c0 = 0; c0 < NC; c0 += 32) {
-                float v[32];
-                tmem_ld32(tlane + (uint32_t)((2 + cb) * TN + c0), v);
-                tmem_ld_wait();
+            for (int ci = 0; ci < NCI; ++ci)
 #pragma unroll
-                for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
-            }
+                for (int c0 = 0; c0 < NC; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tlane + (uint32_t)((2 + ci * NCB + cb) * TN + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
+                }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
@@ -451,14 +462,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
-    } else if (warp == 19) {
-        // ===== CORR issuer (lo*hi + hi*lo), same structure =====
+    } else if (warp >= 19 && warp < 19 + NCI) {
+        // ===== CORR issuer(s): lo*hi + hi*lo into CORR (one warp), or one term and one accumulator per warp =====
+        const int ci = warp - 19;
         const uint32_t idesc = idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, cb = 0;
         uint32_t po = 0, pc0 = 0, pc1 = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const uint32_t d_corr = tb + (uint32_t)((2 + cb) * TN);
+            const uint32_t d_corr = tb + (uint32_t)((2 + ci * NCB + cb) * TN);
             // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
             if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
             else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
@@ -473,8 +485,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) conv2_kernel(const __grid_const
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
                         const uint32_t ta_hi = ta + (uint32_t)(ks * 16), ta_lo = ta_hi + 8;
-                        mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                        const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
+                        if (NCI == 1) {
+                            mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
+                            mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                        } else if (ci == 0) {
+                            mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
+                        } else {
+                            mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, first);
+                        }
                     }
                     mma_commit(OP_EMPTY(so));
                     if (it == nIt - 1) mma_commit(CORR_FULL(cb));
@@ -556,7 +575,7 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cuda
         if (sms <= 0) sms = 148;
     }
     const int grid = q.total_tiles < sms ? q.total_tiles : sms;      // persistent: one CTA per SM walks the tile list
-    conv2_kernel<TN><<<grid, C2_THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+    conv2_kernel<TN><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
     return launch_status("aoc_conv2d_nhwc_tc");
 }
 
