@@ -51,6 +51,61 @@ __global__ void __launch_bounds__(256) channel_stats_partial(const float* __rest
     }
 }
 
+// y = x*a + b (+ res*ra) (ReLU) AND the per-(sample, channel) sum / sum of squares of y in the same pass (the GCT gate /
+// global average pool of the next block then needs no pass of its own).  Same slab decomposition and fixed reduction
+// order as channel_stats_partial; part layout [N][S][2][C] doubles.
+__global__ void __launch_bounds__(256) affine_stats_partial(const float* __restrict__ x, const float* __restrict__ a,
+                                                             const float* __restrict__ b, const float* __restrict__ res,
+                                                             const float* __restrict__ res_scale, float* __restrict__ y,
+                                                             int HW, int C, int ldx, int ldy, int ldres, int relu, int PB,
+                                                             double* __restrict__ part) {
+    extern __shared__ float sm[];  // [PL][2][C]
+    const int n = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    const int Q = C >> 2;
+    const int PL = 256 / Q;
+    const int tid = threadIdx.x;
+    const int q = tid % Q, pl = tid / Q;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
+    if (pl < PL) {
+        const int c = q * 4;
+        const float4 av = ldg4(a + (size_t)n * C + c);
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), rs = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (b) bv = ldg4(b + (size_t)n * C + c);
+        if (res && res_scale) rs = ldg4(res_scale + (size_t)n * C + c);
+        const int pend = min((s + 1) * PB, HW);
+        for (int p = s * PB + pl; p < pend; p += PL) {
+            const size_t pix = (size_t)n * HW + p;
+            const float4 v = ldg4(x + pix * ldx + c);
+            float4 o;
+            if (b) {
+                o.x = fmaf(v.x, av.x, bv.x); o.y = fmaf(v.y, av.y, bv.y);
+                o.z = fmaf(v.z, av.z, bv.z); o.w = fmaf(v.w, av.w, bv.w);
+            } else {
+                o.x = v.x * av.x; o.y = v.y * av.y; o.z = v.z * av.z; o.w = v.w * av.w;
+            }
+            if (res) {
+                float4 r = ldg4(res + pix * ldres + c);
+                if (res_scale) { r.x *= rs.x; r.y *= rs.y; r.z *= rs.z; r.w *= rs.w; }
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(y + pix * ldy + c) = o;
+            sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
+            sq.x = fmaf(o.x, o.x, sq.x); sq.y = fmaf(o.y, o.y, sq.y);
+            sq.z = fmaf(o.z, o.z, sq.z); sq.w = fmaf(o.w, o.w, sq.w);
+        }
+        float* d = sm + (size_t)pl * 2 * C;
+        *reinterpret_cast<float4*>(d + q * 4) = sum;
+        *reinterpret_cast<float4*>(d + C + q * 4) = sq;
+    }
+    __syncthreads();
+    for (int c = tid; c < 2 * C; c += 256) {
+        double acc = 0.0;
+        for (int l = 0; l < PL; ++l) acc += (double)sm[(size_t)l * 2 * C + c];
+        part[(size_t)(n * S + s) * 2 * C + c] = acc;
+    }
+}
+
 // stats: [N][2][C] doubles
 __global__ void channel_stats_final(const double* __restrict__ part, int S, int C2, double* __restrict__ stats) {
     int n = blockIdx.y;
@@ -214,6 +269,30 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
     dim3 g2(cdiv(2 * C, 256), N);
     channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
     return launch_status("aoc_channel_stats_f32");
+}
+
+// y = x*a[n,c] (+ b[n,c]) (+ residual*res_scale[n,c]) (ReLU) with the statistics of y as a by-product.
+// workspace: aoc_channel_stats_workspace_bytes(N, HW, C); stats: [N][2][C] doubles; C <= 1024.
+extern "C" int aoc_affine_stats_nc_f32(const float* x, const float* a, const float* b, const float* residual,
+                                       const float* res_scale, float* y, int N, int HW, int C, int ldx, int ldy,
+                                       int ldres, int relu, double* stats, void* workspace, size_t ws_bytes,
+                                       cudaStream_t stream) {
+    AOC_CHECK_ARG(x && a && y && stats && workspace, "null pointer");
+    AOC_CHECK_ARG(C % 4 == 0 && C >= 4 && C <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (!residual || ldres % 4 == 0),
+                  "C (<= 1024) and the row strides must be multiples of 4");
+    AOC_CHECK_ARG(((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0, "pointers must be 16-byte aligned");
+    AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
+    int PB = stats_slab(HW);
+    int S = cdiv(HW, PB);
+    int PL = 256 / (C / 4);
+    size_t smem = (size_t)PL * 2 * C * sizeof(float);
+    dim3 grid(S, N);
+    double* part = (double*)workspace;
+    affine_stats_partial<<<grid, 256, smem, stream>>>(x, a, b, residual, res_scale, y, HW, C, ldx, ldy, ldres, relu, PB,
+                                                      part);
+    dim3 g2(cdiv(2 * C, 256), N);
+    channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
+    return launch_status("aoc_affine_stats_nc_f32");
 }
 
 extern "C" int aoc_tile_stats_reduce_f32(const float* tile_stats, int N, int tiles_per_image, int C, double* stats,

@@ -236,9 +236,18 @@ class Engine:
         L.channel_stats_f32(x.ptr, x.N, x.HW, x.C, x.ld, _p(phi), _p(thr), st.data_ptr(), ws.data_ptr(), n, self.stream)
         return st
 
-    def affine(self, x, a, b=None, res=None, res_scale=None, relu=False, out=None):
+    def affine(self, x, a, b=None, res=None, res_scale=None, relu=False, out=None, want_stats=False):
+        """y = x*a[n,c] + b[n,c] (+ res*res_scale[n,c]) (ReLU); want_stats -> (y, [N][2][C] statistics of y, same pass)"""
         if out is None:
             out = self.new(x.N, x.H, x.W, x.C)
+        if want_stats:
+            n = self.L.channel_stats_workspace_bytes(x.N, x.HW, x.C)
+            ws = self.ws("stats", n)
+            st = self.empty(x.N * 2 * x.C, torch.float64)
+            self.L.affine_stats_nc_f32(x.ptr, a.data_ptr(), _p(b), None if res is None else res.ptr, _p(res_scale),
+                                       out.ptr, x.N, x.HW, x.C, x.ld, out.ld, 0 if res is None else res.ld,
+                                       1 if relu else 0, st.data_ptr(), ws.data_ptr(), n, self.stream)
+            return out, st
         self.L.affine_nc_f32(x.ptr, a.data_ptr(), _p(b), None if res is None else res.ptr, _p(res_scale), out.ptr,
                              x.N, x.HW, x.C, x.ld, out.ld, 0 if res is None else res.ld, 1 if relu else 0, self.stream)
         return out
@@ -565,10 +574,14 @@ class Engine:
         a = self.linear(head_t, name + ".IA", x.N, act=1, ldx=ldh)
         return self.affine(x, a)
 
-    def gn_bottleneck(self, x, p, stride=1, dil=1):
-        """layers/gct.py:68-91"""
-        gate = self.gct_gate(x, p + ".GCT1")
+    def gn_bottleneck(self, x, p, stride=1, dil=1, pre=None, x_stats=None, want_stats=False):
+        """layers/gct.py:68-91 applied to x*pre[n,c] (pre = the IA gate / conditioning-block scale in front of the
+        block, folded in instead of materialised); x_stats = statistics of x when the producer already has them;
+        want_stats -> (out, statistics of out)"""
         if not self.tc_conv:
+            if pre is not None:
+                x = self.affine(x, pre)
+            gate = self.gct_gate(x, p + ".GCT1")
             y = self.conv(x, p + ".conv1", in_scale=gate)
             y = self.gn(y, p + ".bn1", 32, relu=True)
             y = self.conv(y, p + ".conv2", stride=stride, pad=dil, dil=dil)
@@ -579,9 +592,11 @@ class Engine:
                 r = self.gn(r, p + ".downsample.1", 32)
             else:
                 r = x
-            return self.gn(y, p + ".bn3", 32, relu=True, res=r)
+            out = self.gn(y, p + ".bn3", 32, relu=True, res=r)
+            return (out, self.stats(out)) if want_stats else out
         # tensor-core path: GroupNorm statistics come out of each convolution's epilogue and the normalisation (+ReLU)
         # is applied inside the NEXT convolution's operand path -- the normalised tensors bn1/bn2 never exist in HBM
+        gate = self.gct_gate(x, p + ".GCT1", st=x_stats, pre=pre)         # = pre * GCT gate of (x*pre)
         y1, s1 = self.conv(x, p + ".conv1", in_scale=gate, stats=True)
         a1, b1 = self.gn_ab(y1, p + ".bn1", 32, s1)
         y2, s2 = self.conv(y1, p + ".conv2", stride=stride, pad=dil, dil=dil, in_scale=a1, in_shift=b1, in_relu=True,
@@ -590,14 +605,15 @@ class Engine:
         y3, s3 = self.conv(y2, p + ".conv3", in_scale=a2, in_shift=b2, in_relu=True, stats=True)
         a3, b3 = self.gn_ab(y3, p + ".bn3", 32, s3)
         if (p + ".downsample.0") in self.w.conv:
-            r, sr = self.conv(x, p + ".downsample.0", stride=stride, stats=True)
+            r, sr = self.conv(x, p + ".downsample.0", stride=stride, in_scale=pre, stats=True)
             ar, br = self.gn_ab(r, p + ".downsample.1", 32, sr)
             # relu(GN3(y3) + GN_ds(r)) = relu(y3*a3 + (b3 + br) + r*ar)
-            return self.affine(y3, a3, b3 + br, res=r, res_scale=ar, relu=True)
-        return self.affine(y3, a3, b3, res=x, relu=True)
+            return self.affine(y3, a3, b3 + br, res=r, res_scale=ar, relu=True, want_stats=want_stats)
+        return self.affine(y3, a3, b3, res=x, res_scale=pre, relu=True, want_stats=want_stats)
 
-    def cond_block(self, x, p, beta=0.3):
-        """conditioning_block / conditioning_layer (conditioning_layer.py:24-86) with CL_2/CL_3 folded"""
+    def cond_scale(self, x, p, beta=0.3):
+        """conditioning_block / conditioning_layer (conditioning_layer.py:24-86) with CL_2/CL_3 folded:
+        -> the FiLM scale a[n,c] = 1 + tanh(.) of x -> a*x (the caller folds it into the next block)"""
         L, v = self.L, self.w.vec
         O, hw, C = x.N, x.HW, x.C
         phi = self.empty(O * hw)
@@ -609,29 +625,32 @@ class Engine:
         st = self.stats(x, phi, thr)
         gapm = self.gap(x, st)                                   # masked sum / (h*w)
         c1 = self.linear(gapm, p + ".CL_1.mlp_layer", O)
-        a = self.linear(c1, p + ".fold", O, act=1)
-        return self.affine(x, a)
+        return self.linear(c1, p + ".fold", O, act=1)
 
-    def delta_head(self, x, head):
+    def cond_block(self, x, p, beta=0.3):
+        return self.affine(x, self.cond_scale(x, p, beta))
+
+    def delta_head(self, x, head, st=None):
         """cat([head, sum_objects(GAP(x)) - GAP(x)]) -> [O, 400 + C]"""
         O, C = x.N, x.C
-        px = self.gap(x)
+        px = self.gap(x, st)
         out = self.empty(O * (HEAD + C))
         self.L.copy_channels_f32(head.data_ptr(), out.data_ptr(), O, HEAD, HEAD, HEAD + C, self.stream)
         self.L.delta_sum_f32(px.data_ptr(), out.data_ptr() + 4 * HEAD, O, C, HEAD + C, self.stream)
         return out
 
-    def decoder_aspp(self, x, p):
-        """layers/aspp.py:57-70"""
+    def decoder_aspp(self, x, p, pre=None, x_stats=None):
+        """layers/aspp.py:57-70 applied to x*pre[n,c]"""
         O = x.N
-        st = self.stats(x)
+        st = self.stats(x) if x_stats is None else x_stats
         cat = self.new(O, x.H, x.W, 640)
         for i, d in ((1, 0), (2, 6), (3, 12), (4, 18)):
             q = "%s.aspp%d" % (p, i)
-            gate = self.gct_gate(x, q + ".GCT", st=st)
+            gate = self.gct_gate(x, q + ".GCT", st=st, pre=pre)
             y, s_y = self.conv(x, q + ".atrous_conv", pad=d, dil=max(d, 1), in_scale=gate, stats=True)
             self.gn(y, q + ".bn", 32, relu=True, out=cat.slice(128 * (i - 1), 128), st=s_y)
-        g = T(self.gap(x, st), O, 1, 1, x.C)
+        gp = self.gap(x, st)
+        g = T(gp if pre is None else gp * pre, O, 1, 1, x.C)
         g = self.conv(g, p + ".global_avg_pool.1", relu=True)
         self.resize_bilinear(g, x.H, x.W, out=cat.slice(512, 128))
         gate = self.gct_gate(cat, p + ".GCT")
@@ -644,9 +663,14 @@ class Engine:
         self.copy_channels(x, cat.slice(0, x.C))
         self.copy_channels(mem, cat.slice(x.C, mem.C))
         x = cat
+        st = None
         for i in (1, 2, 3):
-            x = self.ia_gate(x, head, HEAD, "%s.%s_Reweight_Layer_%d" % (p, tag, i))
-            x = self.gn_bottleneck(x, "%s.%s_Bottleneck_%d" % (p, tag, i))
+            a = self.linear(head, "%s.%s_Reweight_Layer_%d.IA" % (p, tag, i), x.N, act=1, ldx=HEAD)     # IA gate, folded
+            name = "%s.%s_Bottleneck_%d" % (p, tag, i)
+            if i < 3:
+                x, st = self.gn_bottleneck(x, name, pre=a, x_stats=st, want_stats=True)
+            else:
+                x = self.gn_bottleneck(x, name, pre=a, x_stats=st)
         return x
 
     def _mem_T(self, m, like):
@@ -665,19 +689,17 @@ class Engine:
         L, v = self.L, self.w.vec
         p = "dynamic_seghead"
         O, h, w = x.N, x.H, x.W
-        x = self.ia_gate(x, head, HEAD, p + ".IA1")
-        x = self.gn_bottleneck(x, p + ".layer1")
-        x = self.cond_block(x, p + ".CLB2")
-        x = self.gn_bottleneck(x, p + ".layer2", 1, 2)
-        x = self.cond_block(x, p + ".CLB3")
-        x = self.gn_bottleneck(x, p + ".layer3", 2, 1)
-        x = self.cond_block(x, p + ".CLB4")
-        x = self.gn_bottleneck(x, p + ".layer4", 1, 2)
-        x = self.cond_block(x, p + ".CLB5")
-        x = self.gn_bottleneck(x, p + ".layer5", 1, 4)
-        dh = self.delta_head(x, head)
-        x = self.ia_gate(x, dh, HEAD + x.C, p + ".IA9")
-        x = self.decoder_aspp(x, p + ".ASPP")
+        # every per-(object, channel) gate of the reference (IA_gate, conditioning_block) is a scale a[n,c] in front
+        # of a block: it is folded into the block (GCT statistics, conv operand path, residual) instead of written out
+        a = self.linear(head, p + ".IA1.IA", O, act=1, ldx=HEAD)
+        x, st = self.gn_bottleneck(x, p + ".layer1", pre=a, want_stats=True)
+        x, st = self.gn_bottleneck(x, p + ".layer2", 1, 2, pre=self.cond_scale(x, p + ".CLB2"), x_stats=st, want_stats=True)
+        x, st = self.gn_bottleneck(x, p + ".layer3", 2, 1, pre=self.cond_scale(x, p + ".CLB3"), x_stats=st, want_stats=True)
+        x, st = self.gn_bottleneck(x, p + ".layer4", 1, 2, pre=self.cond_scale(x, p + ".CLB4"), x_stats=st, want_stats=True)
+        x, st = self.gn_bottleneck(x, p + ".layer5", 1, 4, pre=self.cond_scale(x, p + ".CLB5"), x_stats=st, want_stats=True)
+        dh = self.delta_head(x, head, st)
+        a = self.linear(dh, p + ".IA9.IA", O, act=1, ldx=HEAD + x.C)
+        x = self.decoder_aspp(x, p + ".ASPP", pre=a, x_stats=st)
         cur1 = x
         m0 = self._mem_T(memory[0], cur1) or cur1
         x = self.modulator(x, m0, head, p, "M1")
@@ -695,11 +717,12 @@ class Engine:
         self.copy_channels(xu, cat2.slice(0, 256))
         self.gn(sc, p + ".bn_sc", 16, relu=True, out=cat2.slice(256, 64), st=s_sc)
         x = cat2
-        x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA10")
-        y, s_y = self.conv(x, p + ".conv1", pad=1, stats=True)
-        x = self.gn(y, p + ".bn1", 32, relu=True, st=s_y)
-        x = self.ia_gate(x, self.delta_head(x, head), HEAD + x.C, p + ".IA11")
-        y, s_y = self.conv(x, p + ".conv2", pad=1, stats=True)
+        a = self.linear(self.delta_head(x, head), p + ".IA10.IA", O, act=1, ldx=HEAD + x.C)
+        y, s_y = self.conv(x, p + ".conv1", pad=1, in_scale=a, stats=True)
+        a1, b1 = self.gn_ab(y, p + ".bn1", 32, s_y)
+        x, st = self.affine(y, a1, b1, relu=True, want_stats=True)
+        a = self.linear(self.delta_head(x, head, st), p + ".IA11.IA", O, act=1, ldx=HEAD + x.C)
+        y, s_y = self.conv(x, p + ".conv2", pad=1, in_scale=a, stats=True)
         x = self.gn(y, p + ".bn2", 32, relu=True, st=s_y)
         wfg = self.linear(head, p + ".IA_final_fg", O)
         wbg = self.linear(head, p + ".IA_final_bg", O)

@@ -49,7 +49,7 @@ class AocError(RuntimeError):
 # CUDA kernels launched by one call of each entry point (everything else launches exactly one); used for the
 # `gpu_launches` figure of bench.py.  aoc_kmeans_proxies_f32 launches 1 + 2*iters + 2 (counted by the caller).
 KERNELS_PER_CALL = {
-    "aoc_channel_stats_f32": 2, "aoc_bank_index_build": 4, "aoc_global_match_simt_f32": 2, "aoc_global_match_tc": 10,
+    "aoc_channel_stats_f32": 2, "aoc_affine_stats_nc_f32": 2, "aoc_bank_index_build": 4, "aoc_global_match_simt_f32": 2, "aoc_global_match_tc": 10,
     "aoc_head_pool_f32": 2, "aoc_dyn_logits_f32": 2, "aoc_gemm_tf32x3_test": 3,
     "aoc_version": 0, "aoc_check_device": 0, "aoc_last_error_string": 0, "aoc_set_option": 0, "aoc_conv_tiles_per_image": 0, "aoc_conv_trace": 0,
 }

@@ -107,6 +107,11 @@ int aoc_gap_from_stats_f32(const double* stats, int N, int C, int HW, float* out
 int aoc_affine_nc_f32(const float* x, const float* a, const float* b, const float* residual, const float* res_scale,
                       float* y, int N, int HW, int C, int ldx, int ldy, int ldres, int relu, cudaStream_t stream);
 
+/* same, and the [N][2][C] statistics of y as a by-product of the pass (workspace as for aoc_channel_stats_f32) */
+int aoc_affine_stats_nc_f32(const float* x, const float* a, const float* b, const float* residual,
+                            const float* res_scale, float* y, int N, int HW, int C, int ldx, int ldy, int ldres, int relu,
+                            double* stats, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 /* ---------------------------------------------------------------- FiLM conditioning (film.cu) */
 /* phi_layer: 1x1 conv C->1 (conditioning_layer.py:27) */
 int aoc_cond_phi_f32(const float* x, const float* w, const float* b, float* phi, int N, int HW, int C, int ldx,
