@@ -48,11 +48,17 @@ struct Conv2P {
     int tw_log2, th, tiles_x, tiles_y;
     int ncc, nIt, chunk, taps;
     int tiles_n, total_tiles;
+    int ksplit;             // split-K factor: work item = (tile, K slice); slices write raw partial sums to `ws`
+    float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
     unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event][stage < 256]
     int vec_out;
 };
 
+#ifdef AOC_CONV_TRACE   // tooling build only (tools/conv_trace.py): keeps the production kernel's code small
 #define C2_TRACE(ev, st) do { if (p.trace && blockIdx.x == 0 && (st) < 256) p.trace[(ev) * 256 + (st)] = clock64(); } while (0)
+#else
+#define C2_TRACE(ev, st) do { } while (0)
+#endif
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
@@ -111,7 +117,13 @@ struct C2Cfg {
     static constexpr uint32_t A_TMEM_COL = (2 + NCB * NCI) * TN;   // ring of C2_NO stages x 32 columns behind the accumulators
 };
 
-template <int TN>
+// work item -> output tile and K range.  With split-K (SK; layers that cannot fill the chip with tiles) a work item is
+// (tile, K slice): the slice covers the raw stages [r0, r1) of the (tap, 32-channel box) sequence, i.e. the operand
+// stages [it0, it1).  Without it the K fields are the whole range and fold away (the issue loops of the plain kernel must
+// not carry them: a Tile kept in local memory cost 18 % on the large layers).
+struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0; };
+
+template <int TN, bool SK>
 __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
     using Cfg = C2Cfg<TN>;
     constexpr int C2_NR = Cfg::NR;
@@ -145,9 +157,26 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
     // persistent CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; t -> (pixel tile, output-channel tile) with the
     // channel tile fastest, so CTAs running side by side share the activation patch in L2.  Every role walks the same
     // tile sequence and the rings keep flowing across tile boundaries (the producers run ahead into the next tile).
-    struct Tile { int n, ho0, wo0, n0; };
-    auto decode = [&](int t) {
+    const int nrc = (p.ncc + 1) >> 1;                        // raw (32-channel) stages per tap
+    const int n_items = SK ? p.total_tiles * p.ksplit : p.total_tiles;
+    auto decode = [&](int w) {
         Tile tl;
+        int t = w;
+        if (SK) {
+            t = w / p.ksplit;
+            tl.ks = w - t * p.ksplit;
+            const int R = p.taps * nrc;
+            tl.r0 = R * tl.ks / p.ksplit;
+            tl.r1 = R * (tl.ks + 1) / p.ksplit;
+            int tp = tl.r0 / nrc;
+            tl.tap0 = tp;
+            tl.cc0 = 2 * (tl.r0 - tp * nrc);
+            tl.it0 = tp * p.ncc + tl.cc0;
+            tp = tl.r1 / nrc;
+            tl.it1 = tp * p.ncc + min(2 * (tl.r1 - tp * nrc), p.ncc);
+        } else {
+            tl.ks = 0; tl.r0 = 0; tl.r1 = p.taps * nrc; tl.tap0 = 0; tl.cc0 = 0; tl.it0 = 0; tl.it1 = nIt;
+        }
         const int mt = t / p.tiles_n;
         tl.n0 = (t - mt * p.tiles_n) * TN;
         tl.n = mt / tpi;
@@ -190,7 +219,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
         int gi = 0;                                                          // running operand-stage index (parity = owner)
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
             if (affine && tl.n != tab_n) {
@@ -205,8 +234,8 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 tab_n = tl.n;
             }
-            int tap = 0, cc = 0;
-            for (int it = 0; it < nIt; ++it, ++gi) {
+            int tap = tl.tap0, cc = tl.cc0;
+            for (int it = tl.it0; it < tl.it1; ++it, ++gi) {
                 // both sets walk every raw stage (so neither can lap the producer); only the owner reads its half
                 if ((cc & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
                 if ((gi & 1) == g) {
@@ -276,16 +305,16 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         const int dwp = warp - 8;
         const int q = dwp & 3, half = dwp >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
-        const int nchunks = (nIt + p.chunk - 1) / p.chunk;
         const int m = q * 32 + lane;
         const int ty = m >> p.tw_log2, tx = m & tw_mask;
         int b = 0, cb = 0;
         uint32_t ph0 = 0u, ph1 = 0u, pcf0 = 0u, pcf1 = 0u;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             float acc[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+            const int nchunks = (tl.it1 - tl.it0 + p.chunk - 1) / p.chunk;
             for (int ch = 0; ch < nchunks; ++ch) {
                 if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
                 else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
@@ -324,6 +353,26 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             const int ho = tl.ho0 + ty, wo = tl.wo0 + tx;
             const bool valid = ho < p.Ho && wo < p.Wo;
             const int cbase = tl.n0 + half * NC;
+            if (SK) {
+                // split-K: raw partial sums of this K slice; conv2_splitk_finish_kernel adds the slices in a fixed order
+                if (valid) {
+                    const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
+                    float* dst = p.ws + ((size_t)tl.ks * ((size_t)p.N * p.Ho * p.Wo) + pix) * p.Cout + cbase;
+#pragma unroll
+                    for (int c4 = 0; c4 < NC / 4; ++c4) {
+                        const int co = cbase + c4 * 4;
+                        if (co + 3 < p.Cout) {
+                            *reinterpret_cast<float4*>(dst + c4 * 4) =
+                                make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (co + e < p.Cout) dst[c4 * 4 + e] = acc[c4 * 4 + e];
+                        }
+                    }
+                }
+                continue;
+            }
             {
                 const size_t pix = valid ? ((size_t)tl.n * p.Ho + ho) * p.Wo + wo : 0;
                 float* dst = p.y + pix * p.ldy + cbase;
@@ -374,7 +423,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                     const int stat = i / TN, ch = i - stat * TN;
                     const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
                                       st[(2 * 2 + stat) * TN + ch]) + st[(3 * 2 + stat) * TN + ch];
-                    const int mt = t / p.tiles_n;
+                    const int mt = (SK ? t / p.ksplit : t) / p.tiles_n;
                     if (tl.n0 + ch < p.Cout) p.tile_stats[((size_t)mt * 2 + stat) * p.Cout + tl.n0 + ch] = t4;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -385,19 +434,21 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
             uint32_t pr = 0;
-            const int nrc = (p.ncc + 1) >> 1;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
                 const Tile tl = decode(t);
                 const int wbase = tl.wo0 * p.stride - p.pad, hbase = tl.ho0 * p.stride - p.pad;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int r = tap / p.kw, s = tap - r * p.kw;
-                    for (int rc = 0; rc < nrc; ++rc) {
-                        mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
-                        C2_TRACE(0, 2 * (tap * nrc + rc));
-                        mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
-                        tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil,
-                                    hbase + r * p.dil, tl.n, RAW_FULL(sr));
-                        if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                int tap = tl.tap0, rc = tl.cc0 >> 1;
+                int r = tap / p.kw, s = tap - r * p.kw;
+                for (int rr = tl.r0; rr < tl.r1; ++rr) {
+                    mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
+                    C2_TRACE(0, 2 * rr);
+                    mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
+                    tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil, hbase + r * p.dil,
+                                tl.n, RAW_FULL(sr));
+                    if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                    if (++rc == nrc) {
+                        rc = 0; ++tap;
+                        if (++s == p.kw) { s = 0; ++r; }
                     }
                 }
             }
@@ -407,12 +458,12 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
             int sb_ = 0;
             uint32_t pb = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
                 const Tile tl = decode(t);
                 const int rb = tl.n0 / C2_WRB;
                 const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
-                for (int it = 0; it < nIt; ++it) {
+                for (int it = tl.it0; it < tl.it1; ++it) {
                     mbar_wait(OP_EMPTY(sb_), pb ^ 1u);
                     mbar_arrive_expect_tx(B_FULL(sb_), Cfg::B_BYTES);
                     const uint32_t sb = op0 + sb_ * Cfg::B_BYTES;
@@ -434,9 +485,10 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, b = 0;
         uint32_t po = 0, pe0 = 0, pe1 = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+            const Tile tl = decode(t);
             int in_chunk = 0;
-            for (int it = 0; it < nIt; ++it) {
+            for (int it = tl.it0; it < tl.it1; ++it) {
                 mbar_wait(B_FULL(so), po);
                 if (lane == 0) C2_TRACE(5, it);
                 mbar_wait(OP_FULL(so), po);
@@ -446,7 +498,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                     else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
                 }
                 tc_fence_after();
-                const bool last = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
+                const bool last = (in_chunk + 1 == p.chunk) || (it == tl.it1 - 1);
                 if (elect_one()) {
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
                     const uint32_t d_main = tb + (uint32_t)(b * TN);
@@ -469,12 +521,13 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, cb = 0;
         uint32_t po = 0, pc0 = 0, pc1 = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const uint32_t d_corr = tb + (uint32_t)((2 + ci * NCB + cb) * TN);
             // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
             if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
             else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
-            for (int it = 0; it < nIt; ++it) {
+            const Tile tl = decode(t);
+            for (int it = tl.it0; it < tl.it1; ++it) {
                 mbar_wait(B_FULL(so), po);
                 mbar_wait(OP_FULL(so), po);
                 tc_fence_after();
@@ -485,7 +538,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
                         const uint32_t ta_hi = ta + (uint32_t)(ks * 16), ta_lo = ta_hi + 8;
-                        const uint32_t first = (it > 0 || ks > 0) ? 1u : 0u;
+                        const uint32_t first = (it > tl.it0 || ks > 0) ? 1u : 0u;
                         if (NCI == 1) {
                             mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
                             mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
@@ -496,7 +549,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                         }
                     }
                     mma_commit(OP_EMPTY(so));
-                    if (it == nIt - 1) mma_commit(CORR_FULL(cb));
+                    if (it == tl.it1 - 1) mma_commit(CORR_FULL(cb));
                 }
                 __syncwarp();
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
@@ -509,6 +562,28 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
     if (warp == 18) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// y[m][co] = sum_ks ws[ks][m][co] + bias (+ residual) (ReLU); slices added in index order (deterministic)
+__global__ void conv2_splitk_finish_kernel(const float* __restrict__ ws, int S, long long M, int Cout,
+                                           const float* __restrict__ bias, const float* __restrict__ res, int ldres,
+                                           float* __restrict__ y, int ldy, int relu) {
+    const int C4 = Cout >> 2;
+    const long long total = M * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const long long m = i / C4;
+        float4 a = ldg4(ws + (size_t)m * Cout + c);
+        for (int k = 1; k < S; ++k) {
+            const float4 v = ldg4(ws + ((size_t)k * M + m) * Cout + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (bias) { const float4 b = ldg4(bias + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+        if (res) { const float4 r = ldg4(res + (size_t)m * ldres + c); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
+        if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        *reinterpret_cast<float4*>(y + (size_t)m * ldy + c) = a;
     }
 }
 
@@ -557,11 +632,16 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+constexpr int C2_MAX_KSPLIT = 8;
+int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
+
 template <int TN>
-static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cudaStream_t stream) {
+static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void* workspace, size_t ws_bytes,
+                        cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv2_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
         attr = true;
     }
     Conv2P q = p;
@@ -574,8 +654,32 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, cuda
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    const int grid = q.total_tiles < sms ? q.total_tiles : sms;      // persistent: one CTA per SM walks the tile list
-    conv2_kernel<TN><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+    // split-K: a layer with fewer tiles than half the SMs (the 31x54 maps of the backbone: 14 pixel tiles) would leave
+    // the chip idle and run its whole K loop -- up to 1152 stages -- on a few SMs; slices of >= 4 raw stages (8 operand
+    // stages) spread it.  Needs the caller's workspace for the partial sums; the epilogue fusions (statistics) do not apply.
+    q.ksplit = 1;
+    q.ws = nullptr;
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const int R = p.taps * ((p.ncc + 1) / 2);
+    if (g_conv_splitk && q.total_tiles * 2 <= sms && !p.tile_stats && p.Cout % 4 == 0 && p.vec_out && workspace) {
+        int S = sms / q.total_tiles;
+        if (S > C2_MAX_KSPLIT) S = C2_MAX_KSPLIT;
+        if (S > R / 4) S = R / 4;
+        while (S > 1 && (size_t)S * M * p.Cout * sizeof(float) > ws_bytes) --S;
+        if (S > 1) { q.ksplit = S; q.ws = (float*)workspace; }
+    }
+    const int items = q.total_tiles * q.ksplit;
+    const int grid = items < sms ? items : sms;                       // persistent: one CTA per SM walks the work list
+    if (q.ksplit > 1) {
+        conv2_kernel<TN, true><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+        const long long total4 = M * (p.Cout / 4);
+        int blocks = (int)((total4 + 255) / 256);
+        if (blocks > sms * 8) blocks = sms * 8;
+        conv2_splitk_finish_kernel<<<blocks, 256, 0, stream>>>(q.ws, q.ksplit, M, p.Cout, p.bias, p.res, p.ldres, p.y,
+                                                               p.ldy, p.relu);
+    } else {
+        conv2_kernel<TN, false><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+    }
     return launch_status("aoc_conv2d_nhwc_tc");
 }
 
@@ -621,6 +725,13 @@ static void conv_geometry(int H, int W, int kh, int kw, int stride, int pad, int
     *tw_log2 = best_l2;
 }
 
+extern "C" size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil) {
+    int gH, gW, Ho, Wo, l2;
+    conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
+    if (Ho <= 0 || Wo <= 0) return 0;
+    return (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
+}
+
 extern "C" int aoc_conv_trace(void* device_buffer_8x256_u64) {
     g_conv_trace = (unsigned long long*)device_buffer_8x256_u64;
     return AOC_OK;
@@ -636,7 +747,8 @@ extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride
 extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
                                   const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N,
                                   int H, int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw,
-                                  int stride, int pad, int dil, int relu, int chunk_stages, cudaStream_t stream) {
+                                  int stride, int pad, int dil, int relu, int chunk_stages, void* workspace,
+                                  size_t ws_bytes, cudaStream_t stream) {
     AOC_CHECK_ARG(x && w_packed && y, "null pointer");
     AOC_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && dil > 0, "bad dims");
     AOC_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
@@ -682,8 +794,11 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
         return AOC_EINVAL;
     }
     const int tiles = N * p.tiles_x * p.tiles_y;
-    // narrow N tile when the layer is too small to fill the chip with 128-wide tiles, or when K is so short that the
-    // tile time is its epilogue (the 128-wide epilogue holds 64 accumulators per thread and runs out of registers)
-    const bool narrow = Cout <= 64 || (long long)tiles * cdiv(Cout, 128) < 148 || p.nIt < 32;
-    return narrow ? launch_conv2<64>(map, p, tiles, stream) : launch_conv2<128>(map, p, tiles, stream);
+    // A K = 8 TF32 MMA occupies the tensor pipe ~74 cycles whatever N <= 128, so the 128-wide tile is preferred (half the
+    // instructions per output); the 64-wide one is for Cout <= 64 and for K so short that the tile time is its epilogue
+    // (the 128-wide epilogue holds 64 accumulators per thread and runs out of registers).  Layers with few pixel tiles
+    // are spread over the SMs by split-K, not by narrower tiles.
+    const bool narrow = Cout <= 64 || p.nIt < 32;
+    return narrow ? launch_conv2<64>(map, p, tiles, workspace, ws_bytes, stream)
+                  : launch_conv2<128>(map, p, tiles, workspace, ws_bytes, stream);
 }

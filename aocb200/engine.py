@@ -213,10 +213,14 @@ class Engine:
             if stats:
                 tpi = self.L.conv_tiles_per_image(x.H, x.W, kh, kw, stride, pad, dil)
                 ts = self.empty(x.N * tpi * 2 * Cout)
+            wsp, wsn = None, 0
+            if x.N * Ho * Wo <= 128 * 74 and not stats:       # few pixel tiles: let the library split K
+                wsn = self.L.conv_workspace_bytes(x.N, x.H, x.W, Cout, kh, kw, stride, pad, dil)
+                wsp = self.ws("conv_splitk", wsn).data_ptr()
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
                                   _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
                                   out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
-                                  self.conv_chunk, self.stream)
+                                  self.conv_chunk, wsp, wsn, self.stream)
             if not stats:
                 return out
             st = self.empty(x.N * 2 * Cout, torch.float64)

@@ -181,8 +181,10 @@ def kernel_profile(model, frames, first, device, n_frames):
     conv = prof["aoc_conv2d_nhwc_tc"]
     if conv:
         fl, ms = 0.0, 0.0
+        names = [n for _, n in L.protos["aoc_conv2d_nhwc_tc"][1]]       # argument positions from the header itself
+        ix = [names.index(n) for n in ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil")]
         for e0, e1, a in conv:
-            N, H, W, Cin, Cout, kh, kw, stride, pad, dil = a[8], a[9], a[10], a[11], a[13], a[16], a[17], a[18], a[19], a[20]
+            N, H, W, Cin, Cout, kh, kw, stride, pad, dil = (a[i] for i in ix)
             Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
             Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
             fl += 2.0 * N * Ho * Wo * Cout * kh * kw * Cin

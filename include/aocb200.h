@@ -48,7 +48,8 @@ const char* aoc_last_error_string(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
 int aoc_check_device(int dev);
 /* tuning / diagnostic switches.  "conv_chunk" (default 8): default length, in 16-channel stages, of the TMEM
- * accumulation chains of the tensor-core convolution (see aoc_conv2d_nhwc_tc). */
+ * accumulation chains of the tensor-core convolution (see aoc_conv2d_nhwc_tc).  "conv_splitk" (default 1): allow the
+ * split-K schedule for layers with few output tiles. */
 int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */
@@ -72,7 +73,10 @@ int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int 
 int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
                        const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N, int H,
                        int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad,
-                       int dil, int relu, int chunk_stages, cudaStream_t stream);
+                       int dil, int relu, int chunk_stages, void* workspace, size_t ws_bytes, cudaStream_t stream);
+/* workspace (optional, aoc_conv_workspace_bytes): partial sums for split-K, used when the layer has too few output
+ * tiles to fill the chip (the 31x54 maps of the backbone); without it such layers run unsplit. */
+size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
 /* tile_stats (optional): [N * aoc_conv_tiles_per_image(...)][2][Cout] floats receiving, per 128-pixel output tile, the
  * per-channel sum and sum of squares of the stored output -- the GroupNorm / GCT statistics of the next layer come
  * out of the convolution epilogue instead of a second pass over the tensor (aoc_tile_stats_reduce_f32 folds them into

@@ -113,6 +113,22 @@ def test_conv_tc_vs_fp64(eng):
     c(eng, 2, 25, 33, 100, 64, 3, 1, 1, 1, in_relu=True, seed=118)
 
 
+def test_conv_tc_splitk(eng):
+    """layers with few output tiles (the 31x54 backbone maps) are split along K over the SMs; partial sums are added in
+    a fixed order by a second kernel that also applies bias / residual / ReLU.  Both schedules must meet the bar."""
+    eng.tc_conv = True
+    c = _conv_tc_case
+    for on in (1, 0):
+        assert eng.L.set_option(b"conv_splitk", on) == 0
+        c(eng, 1, 31, 54, 256, 256, 3, 1, 1, 1, relu=True, seed=121)                    # layer3 conv2
+        c(eng, 1, 31, 54, 1024, 256, 1, 1, 0, 1, relu=True, seed=122)                   # layer3 conv1
+        c(eng, 1, 31, 54, 512, 512, 3, 1, 2, 2, relu=True, res=True, seed=123)          # layer4, residual
+        c(eng, 1, 31, 54, 2048, 256, 3, 1, 18, 18, relu=True, seed=124)                 # ASPP d18
+        c(eng, 1, 5, 7, 304, 100, 3, 1, 1, 1, seed=125)                                 # one tile, odd 16-channel tail
+        c(eng, 2, 1, 1, 2048, 256, 1, 1, 0, 1, relu=True, seed=126)                     # image-pool branch
+    eng.L.set_option(b"conv_splitk", 1)
+
+
 def test_conv_tc_chunking(eng):
     """the truncating TMEM accumulation: a single chain over K = 18432 is visibly biased, short chains are not"""
     eng.tc_conv = True

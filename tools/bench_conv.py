@@ -25,6 +25,15 @@ SHAPES = [
     ("dec.half 128->128 3x3 d2 @61x107x6", 6, 61, 107, 128, 128, 3, 1, 2, 2, True),
     ("dec.half 128->512 1x1 @61x107x6", 6, 61, 107, 128, 512, 1, 1, 0, 1, True),
     ("dec.aspp 512->128 3x3 d12 @half x6", 6, 61, 107, 512, 128, 3, 1, 12, 12, True),
+    ("bb.layer1 64->64 3x3 @121x213", 1, 121, 213, 64, 64, 3, 1, 1, 1, False),
+    ("bb.layer1 64->256 1x1 @121x213", 1, 121, 213, 64, 256, 1, 1, 0, 1, False),
+    ("bb.layer1 256->64 1x1 @121x213", 1, 121, 213, 256, 64, 1, 1, 0, 1, False),
+    ("bb.layer2 128->128 3x3 @61x107", 1, 61, 107, 128, 128, 3, 1, 1, 1, False),
+    ("bb.layer2 128->512 1x1 @61x107", 1, 61, 107, 128, 512, 1, 1, 0, 1, False),
+    ("bb.layer2 512->128 1x1 @61x107", 1, 61, 107, 512, 128, 1, 1, 0, 1, False),
+    ("bb.layer4 512->512 3x3 d2 @31x54", 1, 31, 54, 512, 512, 3, 1, 2, 2, False),
+    ("bb.layer4 2048->512 1x1 @31x54", 1, 31, 54, 2048, 512, 1, 1, 0, 1, False),
+    ("bb.layer4 512->2048 1x1 @31x54", 1, 31, 54, 512, 2048, 1, 1, 0, 1, False),
     ("bb.layer3 256->256 3x3 @31x54", 1, 31, 54, 256, 256, 3, 1, 1, 1, False),
     ("bb.layer3 256->1024 1x1 @31x54", 1, 31, 54, 256, 1024, 1, 1, 0, 1, False),
     ("bb.layer3 1024->256 1x1 @31x54", 1, 31, 54, 1024, 256, 1, 1, 0, 1, False),
@@ -48,11 +57,21 @@ def main():
         out = eng.conv(x, name, stride=stride, pad=pad, dil=dil, in_scale=a, in_shift=b, in_relu=aff)
         for _ in range(3):
             eng.conv(x, name, stride=stride, pad=pad, dil=dil, in_scale=a, in_shift=b, in_relu=aff, out=out)
+        # replay from a CUDA graph: the time of back-to-back launches without the host (ctypes + tensor-map encode) in the loop
+        reps = 20
+        cs = torch.cuda.Stream()
+        cs.wait_stream(torch.cuda.current_stream())
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cs):
+            gr.capture_begin()
+            for _ in range(reps):
+                eng.conv(x, name, stride=stride, pad=pad, dil=dil, in_scale=a, in_shift=b, in_relu=aff, out=out)
+            gr.capture_end()
+        torch.cuda.current_stream().wait_stream(cs)
+        gr.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
         e0.record()
-        for _ in range(reps):
-            eng.conv(x, name, stride=stride, pad=pad, dil=dil, in_scale=a, in_shift=b, in_relu=aff, out=out)
+        gr.replay()
         e1.record()
         torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / reps
