@@ -39,6 +39,12 @@ constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_RKC * 4;   // 16384
 constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
 constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
 constexpr int C2_MAX_AFFINE_C = 1024;
+// setmaxnreg targets.  The CTA's registers are fixed at launch (20 warps x 96); an increase can only take what decreases
+// of the same CTA have released, so 8 x 80 (transform) + 8 x 136 (drain) + 4 x 40 (TMA / MMA issue) <= 20 x 96.
+constexpr int C2_REGS_XFORM = 80;
+constexpr int C2_REGS_DRAIN = 136;
+constexpr int C2_REGS_MISC = 40;
+static_assert(8 * C2_REGS_XFORM + 8 * C2_REGS_DRAIN + 4 * C2_REGS_MISC <= 20 * 96, "register budget of the CTA");
 constexpr int C2_THREADS = 672;                         // 8 transform + 8 drain + 2 producer + up to 3 issuer warps
 
 struct Conv2P {
@@ -68,26 +74,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-// v[i] summed over the 32 lanes of the warp, result for index `lane` returned in every lane (transposing butterfly:
-// 31 shuffles instead of 32 x 5; fixed order -> deterministic)
-__device__ __forceinline__ float warp_transpose_sum32(const float* v, int lane) {
-    float a16[16], a8[8], a4[4], a2[2];
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        a16[i] = (h16 ? v[i + 16] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 16], 16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        a8[i] = (h8 ? a16[i + 8] : a16[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a16[i] : a16[i + 8], 8);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        a4[i] = (h4 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h4 ? a8[i] : a8[i + 4], 4);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-        a2[i] = (h2 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h2 ? a4[i] : a4[i + 2], 2);
-    return (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
-}
-
 // What bounds a stage (clock64 trace of the roles, tools/conv_trace.py): ONE thread issuing 6 tcgen05.mma + 2-3
 // tcgen05.commit per stage needs ~45 cycles per instruction, i.e. 400-550 cycles per stage against 384 (TN=128) / 192
 // (TN=64) cycles of tensor work, and the queue behind it is shallow, so the pipe idles during the loop overhead.  The
@@ -95,7 +81,7 @@ __device__ __forceinline__ float warp_transpose_sum32(const float* v, int lane) 
 // accumulator (4 MMAs per stage) -- and a stage's operands are released by one shared barrier (2 commits).
 template <int TN>
 struct C2Cfg {
-    static constexpr int NR = TN <= 64 ? 8 : 6;              // raw activation ring depth (128 pixels x 32 channels each)
+    static constexpr int NR = 6;                             // raw activation ring depth (128 pixels x 32 channels each)
     // operand ring (activation half in TMEM, 32 columns per stage; weight half in shared memory): a weight chunk is
     // requested when the stage it replaces retires and needs an L2 round trip (~1.5k cycles) to land, so the period of
     // a stage cannot drop below (round trip + MMA time) / depth: 8 stages where TMEM has room (TN = 64), else 4
@@ -105,7 +91,8 @@ struct C2Cfg {
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + NO * B_BYTES;
     static constexpr uint32_t STAT_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;    // [4 quadrants][2 stats][TN] floats
-    static constexpr uint32_t BAR_OFF = STAT_OFF + 4 * 2 * TN * 4;
+    static constexpr uint32_t STG_OFF = STAT_OFF + 4 * 2 * TN * 4;             // epilogue staging: 8 warps x 32 rows x 128 B
+    static constexpr uint32_t BAR_OFF = STG_OFF + 8 * 4096;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr int NCB = TN <= 64 ? 2 : 1;             // CORR accumulators: double buffered across tiles when they fit
@@ -205,6 +192,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
         // ===== transform warps: two sets of four (set g owns the operand stages with an even / odd running index, so a
         // set's per-stage instruction stream -- ~550 cycles -- has two stage-times to complete); thread <-> pixel row <->
         // TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
@@ -301,12 +289,14 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         }
     } else if (warp < 16) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
+        // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
+        // tcgen05.ld per thread; the producer / issuer warpgroup gives its share back)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REGS_DRAIN));
         constexpr int NC = TN / 2;
         const int dwp = warp - 8;
         const int q = dwp & 3, half = dwp >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
-        const int m = q * 32 + lane;
-        const int ty = m >> p.tw_log2, tx = m & tw_mask;
+        const uint32_t stg = smem_u32(smem + Cfg::STG_OFF) + (uint32_t)(dwp * 4096);
         int b = 0, cb = 0;
         uint32_t ph0 = 0u, ph1 = 0u, pcf0 = 0u, pcf1 = 0u;
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
@@ -350,86 +340,112 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
             if (NCB == 2) cb ^= 1;
-            const int ho = tl.ho0 + ty, wo = tl.wo0 + tx;
-            const bool valid = ho < p.Ho && wo < p.Wo;
+            // ---- epilogue.  The accumulators sit one pixel row per thread; stored that way every warp store would touch 32
+            // different lines (and the residual loads likewise).  Each warp therefore transposes 32 pixels x 32 channels
+            // through a private, XOR-swizzled 4 KB staging block: on the way back 8 lanes cover the 128 contiguous bytes
+            // of one pixel, so residual loads and output stores are whole 128-byte lines, the bias is one float4 per lane,
+            // and the GroupNorm / GCT statistics need two shuffles per value instead of a 32-lane butterfly.
             const int cbase = tl.n0 + half * NC;
-            if (SK) {
-                // split-K: raw partial sums of this K slice; conv2_splitk_finish_kernel adds the slices in a fixed order
-                if (valid) {
-                    const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
-                    float* dst = p.ws + ((size_t)tl.ks * ((size_t)p.N * p.Ho * p.Wo) + pix) * p.Cout + cbase;
+            const bool partial = SK;                                 // split-K: raw partial sums of this K slice to `ws`
+            float* const ybase = partial ? p.ws + (size_t)tl.ks * ((size_t)p.N * p.Ho * p.Wo) * p.Cout : p.y;
+            const int ldo = partial ? p.Cout : p.ldy;
+            const float* const bias = partial ? nullptr : p.bias;
+            const float* const resb = partial ? nullptr : p.res;
+            const bool relu = !partial && p.relu;
+            const int r_sub = lane >> 3, ch4 = lane & 7;
+            float* st = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);      // [q][stat][TN]
 #pragma unroll
-                    for (int c4 = 0; c4 < NC / 4; ++c4) {
-                        const int co = cbase + c4 * 4;
-                        if (co + 3 < p.Cout) {
-                            *reinterpret_cast<float4*>(dst + c4 * 4) =
-                                make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
+                                 "f"(acc[c0 + 4 * j]), "f"(acc[c0 + 4 * j + 1]), "f"(acc[c0 + 4 * j + 2]), "f"(acc[c0 + 4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+                const int co = cbase + c0 + ch4 * 4;
+                const bool vec = p.vec_out && co + 3 < p.Cout;
+                float b4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (bias) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (co + e < p.Cout) b4[e] = __ldg(bias + co + e);
+                }
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + r_sub;
+                    const int m = q * 32 + r;
+                    const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
+                    const bool valid = ho < p.Ho && wo < p.Wo && co < p.Cout;
+                    float o[4];
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                                 : "r"(stg + (uint32_t)(r * 128 + ((ch4 ^ (r & 7)) << 4))));
+                    if (valid) {
+                        const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
+                        float* dst = ybase + pix * ldo + co;
+                        if (vec) {
+                            if (resb) {
+                                const float4 r4 = ldg4(resb + pix * p.ldres + co);
+                                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                o[e] += b4[e];
+                                if (relu) o[e] = fmaxf(o[e], 0.f);
+                            }
+                            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (co + e < p.Cout) dst[c4 * 4 + e] = acc[c4 * 4 + e];
+                            for (int e = 0; e < 4; ++e) {
+                                if (co + e < p.Cout) {
+                                    if (resb) o[e] += __ldg(resb + pix * p.ldres + co + e);
+                                    o[e] += b4[e];
+                                    if (relu) o[e] = fmaxf(o[e], 0.f);
+                                    dst[e] = o[e];
+                                } else {
+                                    o[e] = 0.f;
+                                }
+                            }
                         }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { s1[e] += o[e]; s2[e] = fmaf(o[e], o[e], s2[e]); }
                     }
                 }
-                continue;
-            }
-            {
-                const size_t pix = valid ? ((size_t)tl.n * p.Ho + ho) * p.Wo + wo : 0;
-                float* dst = p.y + pix * p.ldy + cbase;
-                const float* rsd = p.res ? p.res + pix * p.ldres + cbase : nullptr;
-#pragma unroll
-                for (int c4 = 0; c4 < NC / 4; ++c4) {
-                    const int co = cbase + c4 * 4;
-                    float o[4];
+                __syncwarp();                                        // the staging block is rewritten by the next chunk
+                if (!SK && p.tile_stats) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        o[e] = acc[c4 * 4 + e];
-                        if (valid && co + e < p.Cout) {
-                            if (p.bias) o[e] += __ldg(p.bias + co + e);
-                            if (rsd) o[e] += __ldg(rsd + c4 * 4 + e);
-                            if (p.relu) o[e] = fmaxf(o[e], 0.f);
-                        } else {
-                            o[e] = 0.f;
-                        }
-                        acc[c4 * 4 + e] = o[e];                 // final values (0 outside the image / beyond Cout)
+                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
+                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                     }
-                    if (valid && co < p.Cout) {
-                        if (p.vec_out && co + 3 < p.Cout) {
-                            *reinterpret_cast<float4*>(dst + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
+                    if (lane < 8) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (co + e < p.Cout) dst[c4 * 4 + e] = o[e];
+                        for (int e = 0; e < 4; ++e) {
+                            st[(q * 2 + 0) * TN + half * NC + c0 + ch4 * 4 + e] = s1[e];
+                            st[(q * 2 + 1) * TN + half * NC + c0 + ch4 * 4 + e] = s2[e];
                         }
                     }
                 }
             }
-            if (p.tile_stats) {
+            if (!SK && p.tile_stats) {
                 // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels
-                float* st = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);      // [q][stat][TN]
-#pragma unroll
-                for (int c0 = 0; c0 < NC; c0 += 32) {
-                    const float s1 = warp_transpose_sum32(acc + c0, lane);
-                    float sq[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) sq[e] = acc[c0 + e] * acc[c0 + e];
-                    const float s2 = warp_transpose_sum32(sq, lane);
-                    st[(q * 2 + 0) * TN + half * NC + c0 + lane] = s1;
-                    st[(q * 2 + 1) * TN + half * NC + c0 + lane] = s2;
-                }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 const int i = threadIdx.x - 256;                                 // 0..255 over [stat][TN] (TN <= 128)
                 if (i < 2 * TN) {
                     const int stat = i / TN, ch = i - stat * TN;
                     const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
                                       st[(2 * 2 + stat) * TN + ch]) + st[(3 * 2 + stat) * TN + ch];
-                    const int mt = (SK ? t / p.ksplit : t) / p.tiles_n;
+                    const int mt = t / p.tiles_n;
                     if (tl.n0 + ch < p.Cout) p.tile_stats[((size_t)mt * 2 + stat) * p.Cout + tl.n0 + ch] = t4;
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
     } else if (warp == 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         if (lane == 0) {
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
@@ -454,6 +470,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             }
         }
     } else if (warp == 17) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         if (lane == 0) {
             // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
             int sb_ = 0;
@@ -480,6 +497,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             }
         }
     } else if (warp == 18) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== MAIN issuer (hi*hi): the whole warp runs the (warp-uniform) loop, one elected lane issues =====
         const uint32_t idesc = idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -515,6 +533,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             }
         }
     } else if (warp >= 19 && warp < 19 + NCI) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== CORR issuer(s): lo*hi + hi*lo into CORR (one warp), or one term and one accumulator per warp =====
         const int ci = warp - 19;
         const uint32_t idesc = idesc_tf32(C2_BM, TN);
@@ -634,6 +653,7 @@ static EncodeTiledFn get_encode() {
 
 constexpr int C2_MAX_KSPLIT = 8;
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
+int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
 
 template <int TN>
 static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void* workspace, size_t ws_bytes,
@@ -794,11 +814,11 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
         return AOC_EINVAL;
     }
     const int tiles = N * p.tiles_x * p.tiles_y;
-    // A K = 8 TF32 MMA occupies the tensor pipe ~74 cycles whatever N <= 128, so the 128-wide tile is preferred (half the
-    // instructions per output); the 64-wide one is for Cout <= 64 and for K so short that the tile time is its epilogue
-    // (the 128-wide epilogue holds 64 accumulators per thread and runs out of registers).  Layers with few pixel tiles
-    // are spread over the SMs by split-K, not by narrower tiles.
-    const bool narrow = Cout <= 64 || p.nIt < 32;
+    // A K = 8 TF32 MMA occupies the tensor pipe ~74 cycles whatever N <= 128, and every output-channel tile repeats the
+    // operand transform of its pixels, so the 128-wide tile is used whenever Cout > 64 (its 64 accumulators per drain
+    // thread fit since the warpgroups re-partition the register file).  Layers with few pixel tiles are spread over the
+    // SMs by split-K, not by narrower tiles.
+    const bool narrow = Cout <= 64 || p.nIt < g_conv_narrow_nit;
     return narrow ? launch_conv2<64>(map, p, tiles, workspace, ws_bytes, stream)
                   : launch_conv2<128>(map, p, tiles, workspace, ws_bytes, stream);
 }
