@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         const uint32_t sw = (uint32_t)(pp & 7);                              // TMA SWIZZLE_128B: 16 B chunk ^= row % 8
         const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + Cfg::A_TMEM_COL;
         const bool need_mask = p.in_b != nullptr;
+        const uint32_t tab_s = smem_u32(tab_a);
         int sr = 0, so = 0;
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
@@ -223,6 +224,12 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                 tab_n = tl.n;
             }
             int tap = tl.tap0, cc = tl.cc0;
+            int tr = 0, ts = 0;                                              // filter row / column of `tap` (padding mask)
+            bool ok = true;
+            if (need_mask) {
+                tr = tap / p.kw; ts = tap - tr * p.kw;
+                ok = (unsigned)(hb + tr * p.dil) < (unsigned)p.H && (unsigned)(wb + ts * p.dil) < (unsigned)p.W;
+            }
             for (int it = tl.it0; it < tl.it1; ++it, ++gi) {
                 // both sets walk every raw stage (so neither can lap the producer); only the owner reads its half
                 if ((cc & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
@@ -237,15 +244,15 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                                      : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
                                      : "r"(rawb + (((c8 + j) ^ sw) << 4)));
                     if (affine) {
-                        bool ok = true;
-                        if (need_mask) {
-                            const int r = tap / p.kw, s_ = tap - r * p.kw;
-                            ok = (unsigned)(hb + r * p.dil) < (unsigned)p.H && (unsigned)(wb + s_ * p.dil) < (unsigned)p.W;
-                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(tab_a + cc * C2_KC + j * 4);
-                            const float4 b4 = *reinterpret_cast<const float4*>(tab_b + cc * C2_KC + j * 4);
+                            float4 a4, b4;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                                         : "r"(tab_s + (uint32_t)((cc * C2_KC + j * 4) * 4)));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                                         : "r"(tab_s + (uint32_t)((C2_MAX_AFFINE_C + cc * C2_KC + j * 4) * 4)));
                             v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
                             v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
                         }
@@ -283,7 +290,13 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                     if (lane == 0) mbar_arrive(RAW_EMPTY(sr));
                     if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                 }
-                if (++cc == p.ncc) { cc = 0; ++tap; }
+                if (++cc == p.ncc) {
+                    cc = 0; ++tap;
+                    if (need_mask) {
+                        if (++ts == p.kw) { ts = 0; ++tr; }
+                        ok = (unsigned)(hb + tr * p.dil) < (unsigned)p.H && (unsigned)(wb + ts * p.dil) < (unsigned)p.W;
+                    }
+                }
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
@@ -354,6 +367,13 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
             const bool relu = !partial && p.relu;
             const int r_sub = lane >> 3, ch4 = lane & 7;
             float* st = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);      // [q][stat][TN]
+            int pixi[8];                                             // output pixel of row i * 4 + r_sub (-1: outside)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = q * 32 + i * 4 + r_sub;
+                const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
+                pixi[i] = (ho < p.Ho && wo < p.Wo) ? (tl.n * p.Ho + ho) * p.Wo + wo : -1;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < NC; c0 += 32) {
 #pragma unroll
@@ -374,15 +394,13 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int r = i * 4 + r_sub;
-                    const int m = q * 32 + r;
-                    const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
-                    const bool valid = ho < p.Ho && wo < p.Wo && co < p.Cout;
+                    const bool valid = pixi[i] >= 0 && co < p.Cout;
                     float o[4];
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                  : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
                                  : "r"(stg + (uint32_t)(r * 128 + ((ch4 ^ (r & 7)) << 4))));
                     if (valid) {
-                        const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
+                        const size_t pix = (size_t)pixi[i];
                         float* dst = ybase + pix * ldo + co;
                         if (vec) {
                             if (resb) {
