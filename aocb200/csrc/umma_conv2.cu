@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         return tl;
     };
 
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled onto SMs as this grid's CTAs retire
+    // and run its prologue (barrier init, TMEM allocation, descriptor fetch) under our tail; every role that touches
+    // global memory first executes griddepcontrol.wait (= the previous grid has completed and its writes are visible).
+    asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 17 && lane == 0) {
         for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 8); }
         for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1 + NCI); mbar_init(B_FULL(s), 1); }
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp < 18) asm volatile("griddepcontrol.wait;" ::: "memory");       // transform, drain, TMA producers
 
     if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
@@ -606,6 +611,8 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
 __global__ void conv2_splitk_finish_kernel(const float* __restrict__ ws, int S, long long M, int Cout,
                                            const float* __restrict__ bias, const float* __restrict__ res, int ldres,
                                            float* __restrict__ y, int ldy, int relu) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int C4 = Cout >> 2;
     const long long total = M * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -671,6 +678,7 @@ static EncodeTiledFn get_encode() {
 
 constexpr int C2_MAX_KSPLIT = 8;
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
+int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels
 int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
 
 template <int TN>
@@ -708,15 +716,22 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     }
     const int items = q.total_tiles * q.ksplit;
     const int grid = items < sms ? items : sms;                       // persistent: one CTA per SM walks the work list
+    cudaLaunchAttribute attr_pdl[1];
+    attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C2Cfg<TN>::THREADS); cfg.dynamicSmemBytes = C2Cfg<TN>::SMEM;
+    cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
     if (q.ksplit > 1) {
-        conv2_kernel<TN, true><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, true>, map, q);
         const long long total4 = M * (p.Cout / 4);
         int blocks = (int)((total4 + 255) / 256);
         if (blocks > sms * 8) blocks = sms * 8;
-        conv2_splitk_finish_kernel<<<blocks, 256, 0, stream>>>(q.ws, q.ksplit, M, p.Cout, p.bias, p.res, p.ldres, p.y,
-                                                               p.ldy, p.relu);
+        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+        cudaLaunchKernelEx(&cfg, conv2_splitk_finish_kernel, (const float*)q.ws, q.ksplit, M, p.Cout, p.bias, p.res,
+                           p.ldres, p.y, p.ldy, p.relu);
     } else {
-        conv2_kernel<TN, false><<<grid, C2Cfg<TN>::THREADS, C2Cfg<TN>::SMEM, stream>>>(map, q);
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false>, map, q);
     }
     return launch_status("aoc_conv2d_nhwc_tc");
 }

@@ -160,6 +160,9 @@ class Engine:
         self.tc_conv = tc and os.environ.get("AOCB200_TC_CONV", "1") != "0"
         self.tc_match = tc and os.environ.get("AOCB200_TC_MATCH", "1") != "0"
         self._wpacked = {}
+        for kv in filter(None, os.environ.get("AOCB200_OPTS", "").split(",")):     # e.g. "conv_pdl=0,conv_splitk=0"
+            k, v = kv.split("=")
+            self.L.set_option(k.strip().encode(), int(v))
         self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self.use_graphs = os.environ.get("AOCB200_GRAPHS", "1") != "0"
