@@ -396,7 +396,7 @@ __global__ void head_pool_final_kernel(const float* __restrict__ part, const int
 }
 
 // ------------------------------------------------------------------------------------------------
-// local matching on the half-resolution grid: one warp per query pixel, lanes over channels.
+// local matching on the half-resolution grid: one warp per query pixel, lanes over window columns.
 // ------------------------------------------------------------------------------------------------
 __global__ void row_sqnorm_kernel(const float* __restrict__ x, int rows, float* __restrict__ out) {
     int lane = threadIdx.x & 31;
@@ -413,52 +413,85 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ x, int rows, float* 
 
 constexpr int LM_R = 12;      // cfg.MODEL_MULTI_LOCAL_DISTANCE[-1]
 constexpr int LM_RINGS = 7;   // ring = ceil(chebyshev/2): windows 2,4,..,12 are unions of rings 0..1, 0..2, ...
-__global__ void __launch_bounds__(256) local_match_kernel(const float* __restrict__ xq, const float* __restrict__ yp,
-                                                           const float* __restrict__ x2, const float* __restrict__ y2,
-                                                           const uint8_t* __restrict__ ids, int hh, int ww, int O,
-                                                           const float* __restrict__ bias, float* __restrict__ out,
-                                                           int ld_out) {
-    __shared__ float mins[8][MAXO][LM_RINGS + 1];
+constexpr int LM_Q = 16;                  // query pixels per block: consecutive in x on one row, one warp each
+constexpr int LM_W = LM_Q + 2 * LM_R;     // previous-frame pixels of one window row seen by the block (40)
+constexpr int LM_LD = 101;                // staged row stride: lane <-> pixel reads are bank-conflict free
+
+// order-preserving float <-> int map, so that a shared-memory atomicMin on ints is an exact float minimum
+__device__ __forceinline__ int lm_f2o(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float lm_o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// Windowed correlation without unfold (matching.py:2710-2755): warp = query pixel, LANE = window column.  For each of
+// the <= 25 window rows the block stages the 40 previous-frame pixels its 16 queries can see (one contiguous, coalesced
+// 16 KB read) and every lane runs its own 100-channel dot product out of shared memory (query row broadcast as
+// float4) -- no cross-lane reduction per neighbour, which cost 10 shuffle/add pairs per 4 FMAs in the first version
+// (300 us per call at 61x107).  The per-(object, ring) minima are exact atomic minima in shared memory (order free).
+__global__ void __launch_bounds__(LM_Q * 32) local_match_kernel(const float* __restrict__ xq, const float* __restrict__ yp,
+                                                                const float* __restrict__ x2, const float* __restrict__ y2,
+                                                                const uint8_t* __restrict__ ids, int hh, int ww, int O,
+                                                                const float* __restrict__ bias, float* __restrict__ out,
+                                                                int ld_out) {
+    __shared__ __align__(16) float ys[LM_W * LM_LD];
+    __shared__ __align__(16) float qs[LM_Q][EMB];
+    __shared__ int mins[LM_Q][MAXO][LM_RINGS + 1];
+    __shared__ float y2s[LM_W];
+    __shared__ int ids_s[LM_W];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 8 + warp;
-    if (p >= hh * ww) return;
-    for (int i = lane; i < MAXO * (LM_RINGS + 1); i += 32) (&mins[warp][0][0])[i] = AOC_WRONG_LABEL_PAD;
-    __syncwarp();
-    const int py = p / ww, px = p - py * ww;
-    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane < EMB4) qv = ldg4(xq + (size_t)p * EMB + lane * 4);
-    const float xx = __ldg(x2 + p);
+    const int py = blockIdx.y, px0 = blockIdx.x * LM_Q;
+    const int px = px0 + warp;
+    const bool qvalid = px < ww;
+    const int p = py * ww + px;
+    for (int i = lane; i < MAXO * (LM_RINGS + 1); i += 32) (&mins[warp][0][0])[i] = lm_f2o(AOC_WRONG_LABEL_PAD);
+    if (qvalid && lane < EMB4) *reinterpret_cast<float4*>(&qs[warp][lane * 4]) = ldg4(xq + (size_t)p * EMB + lane * 4);
+    const float xx = qvalid ? __ldg(x2 + p) : 0.f;
     const int y_lo = max(py - LM_R, 0), y_hi = min(py + LM_R, hh - 1);
-    const int x_lo = max(px - LM_R, 0), x_hi = min(px + LM_R, ww - 1);
+    const int sx0 = px0 - LM_R;                                       // image x of staged column 0
+    const int c_lo = max(sx0, 0), c_hi = min(px0 + LM_Q - 1 + LM_R, ww - 1);
+    const int ncol = c_hi - c_lo + 1;
+    const int nx = px - LM_R + lane;                                  // this lane's window column
+    const bool active = qvalid && lane < 2 * LM_R + 1 && nx >= 0 && nx < ww;
+    const int sidx = nx - sx0;
+    const int adx = abs(nx - px);
     for (int ny = y_lo; ny <= y_hi; ++ny) {
-        int ady = abs(ny - py);
-#pragma unroll 4
-        for (int nx = x_lo; nx <= x_hi; ++nx) {
-            int n = ny * ww + nx;
+        __syncthreads();                                              // the previous row has been consumed
+        const size_t row0 = (size_t)ny * ww + c_lo;
+        for (int i = threadIdx.x; i < ncol * EMB4; i += LM_Q * 32) {
+            const int pix = i / EMB4, c4 = i - pix * EMB4;
+            const float4 v = ldg4(yp + (row0 + pix) * EMB + c4 * 4);
+            float* d = ys + (c_lo - sx0 + pix) * LM_LD + c4 * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        if (threadIdx.x < ncol) {
+            y2s[c_lo - sx0 + threadIdx.x] = __ldg(y2 + row0 + threadIdx.x);
+            ids_s[c_lo - sx0 + threadIdx.x] = ids[row0 + threadIdx.x];
+        }
+        __syncthreads();
+        if (active) {
+            const float* yr = ys + sidx * LM_LD;
+            const float4* q4 = reinterpret_cast<const float4*>(&qs[warp][0]);
             float s = 0.f;
-            if (lane < EMB4) {
-                float4 v = ldg4(yp + (size_t)n * EMB + lane * 4);
-                s = qv.x * v.x; s = fmaf(qv.y, v.y, s); s = fmaf(qv.z, v.z, s); s = fmaf(qv.w, v.w, s);
+#pragma unroll 5
+            for (int c4 = 0; c4 < EMB4; ++c4) {
+                const float4 q = q4[c4];
+                s = fmaf(q.x, yr[c4 * 4 + 0], s); s = fmaf(q.y, yr[c4 * 4 + 1], s);
+                s = fmaf(q.z, yr[c4 * 4 + 2], s); s = fmaf(q.w, yr[c4 * 4 + 3], s);
             }
-            s = warp_sum(s);
-            if (lane == 0) {
-                int id = ids[n];
-                if (id < O) {
-                    int ring = (max(ady, abs(nx - px)) + 1) >> 1;
-                    float d = fmaf(-2.0f, s, xx + __ldg(y2 + n));   // (x2 + y2) - 2 x.y   (matching.py:2754)
-                    float* m = &mins[warp][id][ring];
-                    *m = fminf(*m, d);
-                }
+            const int id = ids_s[sidx];
+            if (id < O) {
+                const int ring = (max(abs(ny - py), adx) + 1) >> 1;
+                const float d = fmaf(-2.0f, s, xx + y2s[sidx]);       // (x2 + y2) - 2 x.y   (matching.py:2754)
+                atomicMin(&mins[warp][id][ring], lm_f2o(d));
             }
         }
     }
     __syncwarp();
+    if (!qvalid) return;
     // channel 0 = full window (12), channels 1..5 = windows 2,4,6,8,10   (matching.py:2820-2836)
     for (int i = lane; i < O * 6; i += 32) {
         int o = i / 6, ch = i - o * 6;
         int rmax = ch == 0 ? LM_RINGS - 1 : ch;
         float m = AOC_WRONG_LABEL_PAD;
-        for (int r = 0; r <= rmax; ++r) m = fminf(m, mins[warp][o][r]);
+        for (int r = 0; r <= rmax; ++r) m = fminf(m, lm_o2f(mins[warp][o][r]));
         out[(size_t)p * ld_out + i] = sig2(m + __ldg(bias + o));
     }
 }
@@ -636,8 +669,7 @@ extern "C" int aoc_local_match_f32(const float* xq, const float* yp, const float
                                    int ld_out, cudaStream_t stream) {
     AOC_CHECK_ARG(xq && yp && x2 && y2 && ids && bias && out, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO && hh > 0 && ww > 0 && ld_out >= 6 * O, "bad dims");
-    local_match_kernel<<<cdiv((long long)hh * ww, 8), 256, 0, stream>>>(xq, yp, x2, y2, ids, hh, ww, O, bias, out,
-                                                                        ld_out);
+    local_match_kernel<<<dim3(cdiv(ww, LM_Q), hh), LM_Q * 32, 0, stream>>>(xq, yp, x2, y2, ids, hh, ww, O, bias, out, ld_out);
     return launch_status("aoc_local_match_f32");
 }
 

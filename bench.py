@@ -171,9 +171,12 @@ def kernel_profile(model, frames, first, device, n_frames):
     st = Stepper(model, frames, first, K_OBJ, device, False)   # shapes, just not replayed from the captured graphs
     for _ in range(2):
         st.step()
-    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_kmeans_proxies_f32": []}
+    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_kmeans_proxies_f32": [],
+                 "aoc_affine_stats_nc_f32": [], "aoc_channel_stats_f32": [], "aoc_cond_phi_f32": []}
+    km_rows = []
     for _ in range(n_frames):
         st.step()
+        km_rows.append(sum(eng.bank.index["counts"]) if eng.bank.index else 0)    # bank pixels carrying an object id
     torch.cuda.synchronize()
     prof, L.profile = L.profile, None
     eng.use_graphs = graphs
@@ -200,7 +203,29 @@ def kernel_profile(model, frames, first, device, n_frames):
     km = prof["aoc_kmeans_proxies_f32"]
     if km:
         ms = sum(e0.elapsed_time(e1) for e0, e1, a in km)
-        out["kmeans"] = {"launches": len(km), "ms": ms}
+        names = [n for _, n in L.protos["aoc_kmeans_proxies_f32"][1]]
+        iters = km[0][2][names.index("iters")]
+        # algorithmic bytes of the adaptive-proxy step = iters * (bank rows with an object) * 100 floats
+        out["kmeans"] = {"launches": len(km), "ms": ms, "bytes": float(iters) * sum(km_rows) * 400.0,
+                         "kernels_per_call": 3 + 2 * iters}
+
+    def arg(name, fn, a):
+        return a[[n for _, n in L.protos[fn][1]].index(name)]
+    af = prof["aoc_affine_stats_nc_f32"]
+    if af:       # GroupNorm apply (+ residual, ReLU) with the next block's GCT statistics: 1 read (+1 residual) + 1 write
+        fn = "aoc_affine_stats_nc_f32"
+        by = sum(4.0 * arg("N", fn, a) * arg("HW", fn, a) * arg("C", fn, a) * (3 if arg("residual", fn, a) else 2)
+                 for _, _, a in af)
+        out["affine_stats"] = {"launches": len(af), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in af), "bytes": by,
+                               "kernels_per_call": 2}
+    cs = prof["aoc_channel_stats_f32"] + prof["aoc_cond_phi_f32"]
+    if cs:       # FiLM conditioning layer (phi map pass + masked pooling pass) and the remaining statistics passes: 1 read each
+        by = sum(4.0 * arg("N", "aoc_channel_stats_f32", a) * arg("HW", "aoc_channel_stats_f32", a) *
+                 arg("C", "aoc_channel_stats_f32", a) for _, _, a in prof["aoc_channel_stats_f32"])
+        by += sum(4.0 * arg("N", "aoc_cond_phi_f32", a) * arg("HW", "aoc_cond_phi_f32", a) * arg("C", "aoc_cond_phi_f32", a)
+                  for _, _, a in prof["aoc_cond_phi_f32"])
+        out["film_stats"] = {"launches": len(cs), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in cs), "bytes": by,
+                             "kernels_per_call": 2}
     out["frames"] = n_frames
     return out
 
@@ -308,6 +333,22 @@ def main():
                               "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
                               "note": "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 TF32 MMAs per "
                                       "product (exact mode), so its hardware ceiling is peak/6"}
+        for key, nm, note in (
+                ("kmeans", "kmeans_step/reduce (adaptive object proxies: Lloyd assignment + centroid reduction, no tensor cores)",
+                 "algorithmic bytes = iters x bank rows x 400 B; the rows of a 480p bank fit the 126 MB L2, so a fraction "
+                 "above 1 would be L2-resident traffic, not HBM"),
+                ("affine_stats", "affine_stats_partial (GroupNorm apply + residual + ReLU + next block's statistics)",
+                 "algorithmic bytes = read x (+ residual) + write y"),
+                ("film_stats", "cond_phi / channel_stats_partial (FiLM conditioning: phi map pass, masked pooling pass; GCT statistics)",
+                 "algorithmic bytes = one read of the tensor per pass")):
+            if key in prof:
+                p = prof[key]
+                ach = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+                roofs[key] = {"kernel": nm, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                              "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"] + " HBM copy",
+                              "launches_per_step": p["launches"] * p["kernels_per_call"] / prof["frames"],
+                              "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
+                              "note": note + "; timed per C-ABI call with CUDA events (plain launches)"}
         dom = max(roofs.values(), key=lambda r: r["ms_per_step"]) if roofs else None
         line["roofline"] = dom
         line["roofline_all"] = roofs
