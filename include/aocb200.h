@@ -100,6 +100,9 @@ size_t aoc_channel_stats_workspace_bytes(int N, int HW, int C);
 int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int ldx, const float* phi, const float* thr,
                           double* stats, void* workspace, size_t ws_bytes, cudaStream_t stream);
 /* nn.GroupNorm as y = x*a[n,c] + b[n,c] */
+/* the same coefficients straight from a convolution's tile_stats (aoc_conv2d_nhwc_tc), C / groups <= 32 */
+int aoc_gn_coeffs_tiles_f32(const float* tile_stats, int tiles_per_image, const float* gamma, const float* beta, int N,
+                            int C, int groups, int HW, float eps, float* a, float* b, cudaStream_t stream);
 int aoc_gn_coeffs_f32(const double* stats, const float* gamma, const float* beta, int N, int C, int groups, int HW,
                       float eps, float* a, float* b, cudaStream_t stream);
 /* GCT gate (layers/gct.py:17-36): a[n,c] = pre*(1 + tanh(emb*norm + beta)) */
