@@ -75,12 +75,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: a waiting warp sleeps in hardware until
+        : "memory");                                    // the phase completes instead of re-polling on issue slots
 }
 
 // ---------------------------------------------------------------- TMA bulk copy (global -> shared, mbarrier tx)
@@ -124,6 +124,17 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16 (fp16 operands, fp32 accumulate), A from tensor memory: 16 k elements per instruction, two per 32-bit column
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -193,6 +204,15 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // kind::tf32, fp32 accumulate, A and B K-major, M x N tile (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ inline uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 with fp16 A and B (format code 0), fp32 accumulate, both K-major
+__host__ __device__ inline uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of element (r, k) of a K-major SWIZZLE_NONE block of 16-bit elements (core matrix = 8 rows x 8 elements)
+__host__ __device__ inline uint32_t elem_offset16(int r, int k) {
+    return (uint32_t)((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
 
 }  // namespace umma

@@ -26,6 +26,8 @@
 // fp32-FMA quality.
 #include <cuda.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -37,7 +39,8 @@ constexpr int C2_KC = 16;                               // input channels per op
 constexpr int C2_RKC = 32;                              // input channels per TMA box (128-byte rows)
 constexpr uint32_t C2_RAW_BYTES = C2_BM * C2_RKC * 4;   // 16384
 constexpr int C2_WRB = 128;                             // rows per block of the packed weight image
-constexpr uint32_t C2_WCHUNK = C2_WRB * C2_KC * 4 * 2;  // bytes of one (row block, stage) chunk = 16384
+// bytes of one (row block, stage) weight chunk: 128 rows x 16 channels x {hi, lo}: 3xTF32 16384, split-fp16 8192
+__host__ __device__ constexpr uint32_t c2_wchunk(bool f16) { return C2_WRB * C2_KC * (f16 ? 2u : 4u) * 2u; }
 constexpr int C2_MAX_AFFINE_C = 1024;
 // setmaxnreg targets.  The CTA's registers are fixed at launch (20 warps x 96); an increase can only take what decreases
 // of the same CTA have released, so 8 x 80 (transform) + 8 x 136 (drain) + 4 x 40 (TMA / MMA issue) <= 20 x 96.
@@ -79,14 +82,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 // (TN=64) cycles of tensor work, and the queue behind it is shallow, so the pipe idles during the loop overhead.  The
 // issue work is therefore split over TWO warps -- one feeds the MAIN accumulator (2 MMAs per stage), one the CORR
 // accumulator (4 MMAs per stage) -- and a stage's operands are released by one shared barrier (2 commits).
-template <int TN>
+template <int TN, bool F16>
 struct C2Cfg {
     static constexpr int NR = 6;                             // raw activation ring depth (128 pixels x 32 channels each)
     // operand ring (activation half in TMEM, 32 columns per stage; weight half in shared memory): a weight chunk is
     // requested when the stage it replaces retires and needs an L2 round trip (~1.5k cycles) to land, so the period of
     // a stage cannot drop below (round trip + MMA time) / depth: 8 stages where TMEM has room (TN = 64), else 4
-    static constexpr int NO = TN <= 64 ? 8 : 4;
-    static constexpr uint32_t B_BYTES = TN * C2_KC * 4 * 2;
+    static constexpr int NO = (F16 || TN <= 64) ? 8 : 4;
+    static constexpr uint32_t B_BYTES = TN * C2_KC * (F16 ? 2 : 4) * 2;
+    static constexpr uint32_t A_COLS = F16 ? 16 : 32;        // TMEM columns of one activation operand stage
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + NO * B_BYTES;
@@ -110,9 +114,10 @@ struct C2Cfg {
 // not carry them: a Tile kept in local memory cost 18 % on the large layers).
 struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0; };
 
-template <int TN, bool SK>
-__global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
-    using Cfg = C2Cfg<TN>;
+template <int TN, bool SK, bool F16>
+__global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
+    using Cfg = C2Cfg<TN, F16>;
+    constexpr uint32_t C2_WCHUNK = c2_wchunk(F16);
     constexpr int C2_NR = Cfg::NR;
     constexpr int C2_NO = Cfg::NO, C2_NB = Cfg::NO;
     constexpr int NCB = Cfg::NCB;                            // CORR accumulator buffers (2 when TMEM allows)
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
         int gi = 0;                                                          // running operand-stage index (parity = owner)
+        int pend = -1;                                                       // operand slot stored but not yet published
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
@@ -270,24 +276,46 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                             for (int e = 0; e < 16; ++e) v[e] = 0.f;
                         }
                     }
-                    // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
-                    float o[32];
+                    float o[Cfg::A_COLS];
+                    if (F16) {
+                        // split-fp16 operand: x = hi + 2^-11 * lo with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 mantissa
+                        // bits like the TF32 pair, but one K = 16 MMA per term instead of two K = 8 ones.  Columns of the
+                        // stage: [hi: k0..15, two per column][lo: k0..15]; |x| saturates at the fp16 range (65504).
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        float h, l;
-                        split_tf32(v[e], h, l);
-                        o[(e >> 3) * 16 + (e & 7)] = h;
-                        o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                        for (int j = 0; j < 8; ++j) {
+                            uint32_t h, l;
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l)
+                                : "f"((v[2 * j + 1] - hf.y) * 2048.f), "f"((v[2 * j] - hf.x) * 2048.f));
+                            o[j] = __uint_as_float(h);
+                            o[8 + j] = __uint_as_float(l);
+                        }
+                    } else {
+                        // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float h, l;
+                            split_tf32(v[e], h, l);
+                            o[(e >> 3) * 16 + (e & 7)] = h;
+                            o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                        }
                     }
                     if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(2, it);
+                    // the tensor-memory store of the set's previous stage completes under this stage's ALU work: it is
+                    // waited for and published only now (the MMA side runs >= 4 stages behind, so nothing waits on it)
+                    if (pend >= 0) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(OP_FULL(pend));
+                    }
                     mbar_wait(OP_EMPTY(so), po ^ 1u);
                     if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, it);
                     tc_fence_after();
-                    tmem_st32(a_lane + (uint32_t)(so * 32), o);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(OP_FULL(so));
+                    if (F16) tmem_st16(a_lane + (uint32_t)(so * Cfg::A_COLS), o);
+                    else     tmem_st32(a_lane + (uint32_t)(so * Cfg::A_COLS), o);
+                    pend = so;
                     if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, it);
                 }
                 __syncwarp();
@@ -304,6 +332,12 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                 }
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
+        }
+        if (pend >= 0) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(OP_FULL(pend));
         }
     } else if (warp < 16) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
@@ -352,7 +386,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                     tmem_ld32(tlane + (uint32_t)((2 + ci * NCB + cb) * TN + c0), v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) acc[c0 + e] += v[e];
+                    for (int e = 0; e < 32; ++e) acc[c0 + e] = F16 ? fmaf(v[e], 1.0f / 2048.f, acc[c0 + e]) : acc[c0 + e] + v[e];
                 }
             tc_fence_before();
             __syncwarp();
@@ -512,7 +546,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                         bulk_g2s(sb, src, C2_WCHUNK, B_FULL(sb_));
                     } else {
 #pragma unroll
-                        for (int blk = 0; blk < 4; ++blk)
+                        for (int blk = 0; blk < (F16 ? 2 : 4); ++blk)
                             bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, B_FULL(sb_));
                     }
                     if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
@@ -522,7 +556,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
     } else if (warp == 18) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== MAIN issuer (hi*hi): the whole warp runs the (warp-uniform) loop, one elected lane issues =====
-        const uint32_t idesc = idesc_tf32(C2_BM, TN);
+        const uint32_t idesc = F16 ? idesc_f16(C2_BM, TN) : idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, b = 0;
         uint32_t po = 0, pe0 = 0, pe1 = 0;
@@ -543,9 +577,13 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                 if (elect_one()) {
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
                     const uint32_t d_main = tb + (uint32_t)(b * TN);
-                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32);
-                    mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
-                    mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
+                    if (F16) {
+                        mma_f16_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
+                    } else {
+                        mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
+                        mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                    }
                     mma_commit(OP_EMPTY(so));
                     if (last) mma_commit(MAIN_FULL(b));
                 }
@@ -559,7 +597,7 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== CORR issuer(s): lo*hi + hi*lo into CORR (one warp), or one term and one accumulator per warp =====
         const int ci = warp - 19;
-        const uint32_t idesc = idesc_tf32(C2_BM, TN);
+        const uint32_t idesc = F16 ? idesc_f16(C2_BM, TN) : idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, cb = 0;
         uint32_t po = 0, pc0 = 0, pc1 = 0;
@@ -575,7 +613,12 @@ __global__ void __launch_bounds__(C2Cfg<TN>::THREADS, 1) conv2_kernel(const __gr
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
-                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * 32);
+                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
+                    if (F16) {
+                        // smem stage = [hi block | lo block] of TN rows x 32 B; TMEM stage = [hi: 8 columns | lo: 8 columns]
+                        mma_f16_ts(d_corr, ta + 8, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, it > tl.it0 ? 1u : 0u);
+                        mma_f16_ts(d_corr, ta, smem_desc(sb + TN * 32, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                    } else
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
@@ -652,9 +695,44 @@ __global__ void conv2_pack_weights_kernel(const float* __restrict__ w, int Cout,
         }
         const int rb = r / C2_WRB, rr = r - rb * C2_WRB;
         const int ks = g >> 1, half = g & 1;
-        const size_t base = ((size_t)rb * nIt + it) * C2_WCHUNK + (size_t)ks * 8192 + elem_offset(rr, half * 4);
+        const size_t base = ((size_t)rb * nIt + it) * c2_wchunk(false) + (size_t)ks * 8192 + elem_offset(rr, half * 4);
         *reinterpret_cast<float4*>(out + base) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(out + base + 4096) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// split-fp16 weight image: [row block of 128][stage it = (tap, cc)][hi | lo][128 rows x 16 halves], lo = (w - hi) * 2^11
+__global__ void conv2_pack_weights_f16_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ncc,
+                                              int rows_padded, uint8_t* __restrict__ out) {
+    const int nIt = taps * ncc;
+    const long long total = (long long)rows_padded * nIt * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i % rows_padded);
+        const long long rest = i / rows_padded;
+        const int g = (int)(rest & 1);                  // 8-channel granule (one 16-byte core-matrix row) of the stage
+        const int it = (int)(rest >> 1);
+        const int tap = it / ncc, cc = it - tap * ncc;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ci = cc * C2_KC + g * 8 + e * 2 + h;
+                const float v = (r < Cout && ci < Cin) ? __ldg(w + ((size_t)r * taps + tap) * Cin + ci) : 0.f;
+                x[h] = fminf(fmaxf(v, -65504.f), 65504.f);
+            }
+            const __half2 hh = __floats2half2_rn(x[0], x[1]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn((x[0] - hf.x) * 2048.f, (x[1] - hf.y) * 2048.f);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const int rb = r / C2_WRB, rr = r - rb * C2_WRB;
+        const size_t base = ((size_t)rb * nIt + it) * c2_wchunk(true) + elem_offset16(rr, g * 8);
+        *reinterpret_cast<uint4*>(out + base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(out + base + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -678,16 +756,18 @@ static EncodeTiledFn get_encode() {
 
 constexpr int C2_MAX_KSPLIT = 8;
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
+int g_conv_f16 = 1;      // aoc_set_option("conv_f16", 0/1): split-fp16 operands (2 terms, K = 16 MMAs) instead of 3xTF32.
+                         // Read by the weight packer AND the convolution: switch it before any weight is packed.
 int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels
 int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
 
-template <int TN>
+template <int TN, bool F16>
 static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void* workspace, size_t ws_bytes,
                         cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(conv2_kernel<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
-        cudaFuncSetAttribute(conv2_kernel<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
         attr = true;
     }
     Conv2P q = p;
@@ -720,10 +800,10 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C2Cfg<TN>::THREADS); cfg.dynamicSmemBytes = C2Cfg<TN>::SMEM;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C2Cfg<TN, F16>::THREADS); cfg.dynamicSmemBytes = C2Cfg<TN, F16>::SMEM;
     cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
     if (q.ksplit > 1) {
-        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, true>, map, q);
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, true, F16>, map, q);
         const long long total4 = M * (p.Cout / 4);
         int blocks = (int)((total4 + 255) / 256);
         if (blocks > sms * 8) blocks = sms * 8;
@@ -731,7 +811,7 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
         cudaLaunchKernelEx(&cfg, conv2_splitk_finish_kernel, (const float*)q.ws, q.ksplit, M, p.Cout, p.bias, p.res,
                            p.ldres, p.y, p.ldy, p.relu);
     } else {
-        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false>, map, q);
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false, F16>, map, q);
     }
     return launch_status("aoc_conv2d_nhwc_tc");
 }
@@ -745,7 +825,7 @@ using namespace aoc;
 
 extern "C" size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw) {
     const size_t ncc = (size_t)cdiv(Cin, C2_KC);
-    return (size_t)cdiv(Cout, C2_WRB) * kh * kw * ncc * C2_WCHUNK;
+    return (size_t)cdiv(Cout, C2_WRB) * kh * kw * ncc * c2_wchunk(g_conv_f16 != 0);
 }
 
 extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
@@ -753,10 +833,13 @@ extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, i
     AOC_CHECK_ARG(w && w_packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "bad args");
     const int ncc = cdiv(Cin, C2_KC);
     const int rows_padded = cdiv(Cout, C2_WRB) * C2_WRB;
-    const long long total = (long long)rows_padded * kh * kw * ncc * 4;
+    const long long total = (long long)rows_padded * kh * kw * ncc * (g_conv_f16 ? 2 : 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    conv2_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
+    if (g_conv_f16)
+        conv2_pack_weights_f16_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
+    else
+        conv2_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
     return launch_status("aoc_conv_pack_weights_tf32x3");
 }
 
@@ -852,6 +935,9 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     // thread fit since the warpgroups re-partition the register file).  Layers with few pixel tiles are spread over the
     // SMs by split-K, not by narrower tiles.
     const bool narrow = Cout <= 64 || p.nIt < g_conv_narrow_nit;
-    return narrow ? launch_conv2<64>(map, p, tiles, workspace, ws_bytes, stream)
-                  : launch_conv2<128>(map, p, tiles, workspace, ws_bytes, stream);
+    if (g_conv_f16)
+        return narrow ? launch_conv2<64, true>(map, p, tiles, workspace, ws_bytes, stream)
+                      : launch_conv2<128, true>(map, p, tiles, workspace, ws_bytes, stream);
+    return narrow ? launch_conv2<64, false>(map, p, tiles, workspace, ws_bytes, stream)
+                  : launch_conv2<128, false>(map, p, tiles, workspace, ws_bytes, stream);
 }
