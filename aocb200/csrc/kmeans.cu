@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(256) kmeans_step_kernel(const float* __restric
             Cs[c * KM_K + j] = cent[(size_t)o * KM_K * EMB + i];
         }
     }
-    for (int i = tid; i < KM_K * EMB; i += 256) acc[i] = 0.f;
     __syncthreads();
     if (ASSIGN) {
         if (tid < KM_K) {
@@ -141,23 +140,48 @@ __global__ void __launch_bounds__(256) kmeans_step_kernel(const float* __restric
         if (tid < KM_TILE) lab[tid] = (tid < nrow) ? labels[seg + t0 + tid] : -1;
     }
     __syncthreads();
-    // ---- 3. per-label column sums in row order: thread (label parity g, channel c)
+    // ---- 3. per-label column sums in row order.  The rows of the tile are first counting-sorted by label (stable: warp
+    // ballots give each row its rank among the rows of its label), then thread (label j, channel c) adds the rows of
+    // label j in increasing row order into a REGISTER -- the same summation order as a read-modify-write per row on a
+    // shared accumulator, without its store-to-load latency chain (which was ~60 % of the kernel's time).
     {
-        const int g = tid >> 7, c = tid & 127;
-        if (c < EMB) {
-            for (int r = 0; r < nrow; ++r) {
-                const int l = lab[r];
-                if ((l & 1) == g) acc[l * EMB + c] += tile[r * KM_LD + c];
+        int* order = reinterpret_cast<int*>(acc);                    // [KM_TILE] row ids grouped by label
+        int* wcnt = order + KM_TILE;                                 // [4 warps][KM_K] rows of label j in warp w
+        int* start = wcnt + 4 * KM_K;                                // [KM_K + 1]
+        int l = -1, rank = 0;
+        if (tid < KM_TILE) {
+            l = lab[tid];
+#pragma unroll
+            for (int j = 0; j < KM_K; ++j) {
+                const unsigned m = __ballot_sync(0xffffffffu, l == j);
+                if (l == j) rank = __popc(m & ((1u << lane) - 1u));
+                if (lane == 0) wcnt[warp * KM_K + j] = __popc(m);
             }
         }
-    }
-    __syncthreads();
-    const size_t pbase = ((size_t)o * nb_max + b) * KM_K;
-    for (int i = tid; i < KM_K * EMB; i += 256) part[pbase * EMB + i] = acc[i];
-    if (tid < KM_K) {
-        int n = 0;
-        for (int r = 0; r < nrow; ++r) n += (lab[r] == tid);
-        pcnt[pbase + tid] = n;
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int j = 0; j < KM_K; ++j) {
+                start[j] = run;
+                run += wcnt[j] + wcnt[KM_K + j] + wcnt[2 * KM_K + j] + wcnt[3 * KM_K + j];
+            }
+            start[KM_K] = run;
+        }
+        __syncthreads();
+        if (l >= 0) {
+            int pos = start[l] + rank;
+            for (int w = 0; w < warp; ++w) pos += wcnt[w * KM_K + l];
+            order[pos] = tid;
+        }
+        __syncthreads();
+        const size_t pbase = ((size_t)o * nb_max + b) * KM_K;
+        for (int i = tid; i < KM_K * EMB; i += 256) {
+            const int j = i / EMB, c = i - j * EMB;
+            float a = 0.f;
+            for (int q = start[j]; q < start[j + 1]; ++q) a += tile[order[q] * KM_LD + c];
+            part[pbase * EMB + i] = a;
+        }
+        if (tid < KM_K) pcnt[pbase + tid] = start[tid + 1] - start[tid];
     }
 }
 
