@@ -268,7 +268,8 @@ def main():
                           "%d timed predicted frames, memory bank +1 frame every %d, one independent clip per GPU"
                           % (H, W, K_OBJ, args.warmup, args.steps, MEM_EVERY),
               "l2": "no flush: per-step working set (>300 MB of activations + bank) exceeds the 126 MB L2",
-              "precision": "fp32 I/O; tensor-core kernels use 3xTF32 (fp32-faithful), fp32 accumulate"}
+              "precision": "fp32 I/O; fp32-faithful tensor-core kernels: convolution = split-fp16 operand pairs (22 mantissa bits, "
+                           "3 kind::f16 MMAs per product), matching = 3xTF32; fp32 accumulate"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -332,17 +333,23 @@ def main():
         prof = kernel_profile(model, frames, first, device, min(6, args.steps))
         step_ms = ms / args.steps
         roofs = {}
-        for key, nm in (("conv", "conv_tc_kernel (tcgen05 implicit-GEMM conv, 3xTF32)"),
-                        ("match", "match_tc_kernel (tcgen05 global matching, 3xTF32)")):
+        for key, nm, ceil, note, traffic in (
+                ("conv", "conv2_kernel (tcgen05 implicit-GEMM convolution, split-fp16 operands)", 3.0,
+                 "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 kind::f16 MMAs per product (hi*hi, lo*hi, "
+                 "hi*lo), so its hardware ceiling is peak/3; traffic = DRAM bytes of the largest layer's launch (decoder conv1, "
+                 "algorithmic 277 MB) from profiles/r1_conv2_dec_conv1_f16_ncu_full.txt", 255374592),
+                ("match", "match_tc_kernel (tcgen05 global matching, 3xTF32)", 6.0,
+                 "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 TF32 MMAs per product at half the bf16 "
+                 "rate, so its hardware ceiling is peak/6", None)):
             if key in prof:
                 p = prof[key]
                 ach = p["flop"] / (p["ms"] * 1e-3) / 1e12
                 roofs[key] = {"kernel": nm, "bound": "tensor", "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                              "frac": ach / pk["tensor"], "traffic": None, "peak_source": pk["src"] + " bf16 dense, sustained",
+                              "frac": ach / pk["tensor"], "frac_of_exact_mode_ceiling": ach / (pk["tensor"] / ceil),
+                              "traffic": traffic, "peak_source": pk["src"] + " bf16 dense, sustained",
                               "launches_per_step": p["launches"] / prof["frames"],
                               "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
-                              "note": "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 TF32 MMAs per "
-                                      "product (exact mode), so its hardware ceiling is peak/6"}
+                              "note": note}
         for key, nm, note in (
                 ("kmeans", "kmeans_step/reduce (adaptive object proxies: Lloyd assignment + centroid reduction, no tensor cores)",
                  "algorithmic bytes = iters x bank rows x 400 B; the rows of a 480p bank fit the 126 MB L2, so a fraction "
