@@ -75,12 +75,26 @@ __global__ void __launch_bounds__(256) kmeans_step_kernel(const float* __restric
     const int nrow = min(KM_TILE, n_o - t0);
 
     // ---- 1. stage the tile: warp w loads rows w, w+8, ... (25 lanes x 16 B = one 400 B row per instruction)
-    for (int r = warp; r < nrow; r += 8) {
-        const int srow = INDIRECT ? __ldg(nat2sorted + t0 + r) : (seg + t0 + r);
-        if (lane < EMB4) {
-            float4 v = ldg4(S + (size_t)srow * EMB + lane * 4);
-            float* d = tile + r * KM_LD + lane * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    // (eight rows per batch: all loads are issued before the first store, one L2 round trip per batch instead of per row)
+#pragma unroll
+    for (int batch = 0; batch < KM_TILE / 64; ++batch) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = warp + 8 * (batch * 8 + i);
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrow && lane < EMB4) {
+                const int srow = INDIRECT ? __ldg(nat2sorted + t0 + r) : (seg + t0 + r);
+                v[i] = ldg4(S + (size_t)srow * EMB + lane * 4);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = warp + 8 * (batch * 8 + i);
+            if (r < nrow && lane < EMB4) {
+                float* d = tile + r * KM_LD + lane * 4;
+                d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+            }
         }
     }
     if (ASSIGN) {
@@ -206,13 +220,24 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int n = 0;
     if (j < k) {
-        for (int b = warp; b < nb; b += 8) {
-            const size_t pbase = ((size_t)o * nb_max + b) * KM_K + j;
-            if (lane < EMB4) {
-                float4 v = ldg4(part + pbase * EMB + lane * 4);
-                s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+        // four slabs per iteration, loads issued together (the loop was one L2 round trip per slab); same order of adds
+        for (int b0 = warp; b0 < nb; b0 += 32) {
+            float4 v[4];
+            int c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b = b0 + 8 * u;
+                const size_t pbase = ((size_t)o * nb_max + (b < nb ? b : b0)) * KM_K + j;
+                v[u] = (b < nb && lane < EMB4) ? ldg4(part + pbase * EMB + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                c[u] = b < nb ? __ldg(pcnt + pbase) : 0;
             }
-            n += __ldg(pcnt + pbase);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (b0 + 8 * u < nb) {
+                    s0 += (double)v[u].x; s1 += (double)v[u].y; s2 += (double)v[u].z; s3 += (double)v[u].w;
+                    n += c[u];
+                }
+            }
         }
     }
     if (lane < EMB4) {

@@ -171,6 +171,11 @@ class Engine:
         for kv in filter(None, os.environ.get("AOCB200_OPTS", "").split(",")):     # e.g. "conv_pdl=0,conv_splitk=0"
             k, v = kv.split("=")
             self.L.set_option(k.strip().encode(), int(v))
+        # the split-fp16 convolution operands saturate at the fp16 range: weights (FrozenBatchNorm folded in) that do
+        # not fit select the 3xTF32 operand mode for this process (same kernels and tests, ~12 % slower)
+        wmax = max(float(w.abs().max()) for w, _, _ in self.w.conv.values())
+        if not (wmax < 6.0e4):
+            self.L.set_option(b"conv_f16", 0)
         self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self.use_graphs = os.environ.get("AOCB200_GRAPHS", "1") != "0"
