@@ -220,24 +220,13 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int n = 0;
     if (j < k) {
-        // four slabs per iteration, loads issued together (the loop was one L2 round trip per slab); same order of adds
-        for (int b0 = warp; b0 < nb; b0 += 32) {
-            float4 v[4];
-            int c[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int b = b0 + 8 * u;
-                const size_t pbase = ((size_t)o * nb_max + (b < nb ? b : b0)) * KM_K + j;
-                v[u] = (b < nb && lane < EMB4) ? ldg4(part + pbase * EMB + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                c[u] = b < nb ? __ldg(pcnt + pbase) : 0;
+        for (int b = warp; b < nb; b += 8) {
+            const size_t pbase = ((size_t)o * nb_max + b) * KM_K + j;
+            if (lane < EMB4) {
+                float4 v = ldg4(part + pbase * EMB + lane * 4);
+                s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (b0 + 8 * u < nb) {
-                    s0 += (double)v[u].x; s1 += (double)v[u].y; s2 += (double)v[u].z; s3 += (double)v[u].w;
-                    n += c[u];
-                }
-            }
+            n += __ldg(pcnt + pbase);
         }
     }
     if (lane < EMB4) {

@@ -838,6 +838,13 @@ class Engine:
             self._segA[(H, W)] = segA
         else:
             segA["img"].copy_(current_frame, non_blocking=True)
+        # The bank index (and its one host synchronisation, when the bank changed) does not depend on the current frame:
+        # it is brought up to date BEFORE the backbone is launched, so that the host's share of a bank change (RNG draws,
+        # re-capture of segment F) runs under the backbone instead of leaving the GPU idle behind a drained stream.
+        ix_early = None
+        if prev_embedding is not None:
+            ix_early = self._bank_index(ref_embeddings, ref_masks, segA["emb"].H, segA["emb"].W,
+                                        self._num_objects(gt_ids) + 1)
         segA["graph"].replay()
         emb, low = segA["emb"], segA["low"]
         h, w, hw = emb.H, emb.W, emb.HW
@@ -863,7 +870,7 @@ class Engine:
                             for _ in range(4)], turn=0, segF=None, segC={})
             self._static[keyS] = st
         # ---- bank index (host sync only when the bank changed) and this frame's RNG draws
-        ix = self._bank_index(ref_embeddings, ref_masks, h, w, O)
+        ix = ix_early
         kk, init = self._draw_kmeans_init(ix, O)
         hbuf, hev = st["host"][st["turn"] % 4]
         st["turn"] += 1
