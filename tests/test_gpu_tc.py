@@ -129,6 +129,23 @@ def test_conv_tc_splitk(eng):
     eng.L.set_option(b"conv_splitk", 1)
 
 
+def test_conv_tc_tf32_mode(eng):
+    """the 3xTF32 operand mode stays in the library for weights / activations beyond the fp16 range (the engine selects
+    it when a folded weight exceeds 6e4): same bar as the default split-fp16 mode, including values fp16 cannot hold"""
+    eng.tc_conv = True
+    c = _conv_tc_case
+    try:
+        assert eng.L.set_option(b"conv_f16", 0) == 0
+        eng._wpacked.clear()                                    # the packed weight image depends on the operand mode
+        c(eng, 1, 31, 54, 256, 256, 3, 1, 1, 1, relu=True, seed=131)
+        c(eng, 2, 25, 33, 128, 512, 1, 1, 0, 1, scale=True, shift=True, in_relu=True, bias=False, seed=132)
+        c(eng, 1, 121, 213, 64, 64, 3, 1, 1, 1, relu=True, res=True, seed=133)
+        c(eng, 1, 31, 54, 2048, 256, 3, 1, 12, 12, relu=True, seed=134)
+    finally:
+        eng.L.set_option(b"conv_f16", 1)
+        eng._wpacked.clear()
+
+
 def test_conv_tc_chunking(eng):
     """the truncating TMEM accumulation: a single chain over K = 18432 is visibly biased, short chains are not"""
     eng.tc_conv = True
