@@ -9,6 +9,8 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31).  Accumulators are double-buffered in TMEM
 // (2 x 256 columns) so the epilogue of bank block i overlaps the MMAs of block i+1.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -16,14 +18,23 @@ namespace aoc {
 using namespace umma;
 
 constexpr int MAXO_ = AOC_MAX_OBJECTS;
-constexpr int TC_K = 104;              // embedding width 100 zero-padded to a multiple of 8
+constexpr int TC_K = 104;              // embedding width 100 zero-padded to a multiple of 8 (3xTF32 images)
 constexpr int TC_KS = TC_K / KSTEP;    // 13 k-steps
 constexpr int QB = 128;                // query rows per CTA (= TMEM lanes)
 constexpr int RBK = 256;               // bank rows per MMA (N)
 constexpr int NST = 6;                 // smem pipeline stages (one (row block, k-step) chunk each)
-constexpr uint32_t A_BYTES = TC_KS * 2 * QB * KSTEP * 4;     // 106496
-constexpr uint32_t B_STAGE = 2 * RBK * KSTEP * 4;            // 16384
-constexpr uint32_t SMEM_MATCH = A_BYTES + NST * B_STAGE + 256;
+constexpr uint32_t B_STAGE = 2 * RBK * KSTEP * 4;            // 16384: hi + lo block of one k-step (32 B per row and term)
+// operand format of the contraction: 3xTF32 (13 k-steps of 8 floats) or split-fp16 (7 k-steps of 16 halves; hi = fp16(x),
+// lo = fp16(x - hi) UNscaled: centred embeddings are O(1), so lo keeps >= 2^-24 absolute accuracy and all three products
+// share one accumulator).  Same bytes per k-step and term, so both formats use the same pipeline; fp16 needs 21 instead
+// of 39 tensor instructions per 256 bank rows and streams 54 % of the bank bytes from L2.
+template <bool F16> struct MatchFmt {
+    static constexpr int KS = F16 ? 7 : TC_KS;
+    static constexpr uint32_t A_BYTES = KS * 2 * QB * KSTEP * 4;
+    static constexpr uint32_t SMEM = A_BYTES + NST * B_STAGE + 256;
+};
+constexpr uint32_t A_BYTES = MatchFmt<false>::A_BYTES;       // 106496 (self-test path)
+constexpr uint32_t SMEM_MATCH = MatchFmt<false>::SMEM;
 
 // x [R][ld] fp32 (first K_valid columns used, zero beyond; rows >= R zero) -> tc image with row blocks of RB rows,
 // K = ksteps*8 columns.  One thread per (row, float4 granule).
@@ -59,14 +70,51 @@ __global__ void pack_tc_image_kernel(const float* __restrict__ x, int R, int K_v
     }
 }
 
+// split-fp16 image of x - center: one thread per (row, granule of 8 halves); chunk (rb, ks) = [hi block][lo block]
+__global__ void pack_tc_image_f16_kernel(const float* __restrict__ x, int R, int K_valid, int ld, int RB, int ksteps,
+                                         long long rows_padded, uint8_t* __restrict__ out,
+                                         const float* __restrict__ center, const float* __restrict__ valid_r2) {
+    long long total = rows_padded * ksteps * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i % rows_padded;
+        int g = (int)(i / rows_padded);           // granule index: k = 8*g
+        int ks = g >> 1, half = g & 1;
+        uint32_t hi[4], lo[4];
+        const bool live = r < R && !(valid_r2 && isinf(__ldg(valid_r2 + r)));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int k = g * 8 + e * 2 + h;
+                if (live && k < K_valid) v[h] = __ldg(x + (size_t)r * ld + k) - (center ? __ldg(center + k) : 0.f);
+                v[h] = fminf(fmaxf(v[h], -65504.f), 65504.f);
+            }
+            const __half2 hh = __floats2half2_rn(v[0], v[1]);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(v[0] - hf.x, v[1] - hf.y);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        long long rb = r / RB;
+        int rr = (int)(r - rb * RB);
+        size_t base = ((size_t)rb * ksteps + ks) * chunk_bytes(RB) + elem_offset16(rr, half * 8);
+        *reinterpret_cast<uint4*>(out + base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(out + base + block_bytes(RB)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test)
-template <int MODE>
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restrict__ Qimg,
                                                           const uint8_t* __restrict__ Simg,
                                                           const float* __restrict__ q2, const float* __restrict__ r2,
                                                           const int* __restrict__ meta, int O, int HW, int nrb_total,
                                                           int nsplit, float* __restrict__ mins, float* __restrict__ C,
                                                           int ldc, uint32_t lbo, uint32_t sbo) {
+    constexpr int TC_KS = MatchFmt<F16>::KS;
+    constexpr uint32_t A_BYTES = MatchFmt<F16>::A_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + A_BYTES;
@@ -123,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
     } else if (warp == 1) {
         if (rb1 > rb0) {
             // ===== MMA issuer: warp-uniform loop, one elected lane issues (operands stay in uniform registers) =====
-            const uint32_t idesc = idesc_tf32(QB, RBK);
+            const uint32_t idesc = F16 ? idesc_f16(QB, RBK) : idesc_tf32(QB, RBK);
             const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
             mbar_wait(A_FULL, 0);
             tc_fence_after();
@@ -144,9 +192,15 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                         const uint32_t b_lo = b_hi + RBK * KSTEP * 4;
                         const uint64_t dah = smem_desc(a_hi, lbo, sbo), dal = smem_desc(a_lo, lbo, sbo);
                         const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
-                        mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-                        mma_tf32(d, dah, dbl, idesc, 1u);
-                        mma_tf32(d, dah, dbh, idesc, 1u);
+                        if (F16) {
+                            mma_f16(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                            mma_f16(d, dah, dbl, idesc, 1u);
+                            mma_f16(d, dah, dbh, idesc, 1u);
+                        } else {
+                            mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                            mma_tf32(d, dah, dbl, idesc, 1u);
+                            mma_tf32(d, dah, dbh, idesc, 1u);
+                        }
                         mma_commit(EMPTY(stage));
                         if (ks == TC_KS - 1) mma_commit(TFULL(as));
                     }
@@ -165,15 +219,15 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
         int as = 0;
         uint32_t aphase = 0;
         int cur = 0;
-        float m = INFINITY;
+        float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;   // four independent chains of the running minimum
         if (MODE == 0) {
             while (cur < O - 1 && rb0 * RBK >= seg[cur + 1]) ++cur;
         }
         for (int rb = rb0; rb < rb1; ++rb) {
             if (MODE == 0) {
                 if (rb * RBK >= seg[cur + 1]) {   // crossed into the next object's segment: flush
-                    if (qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = m;
-                    m = INFINITY;
+                    if (qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = fminf(fminf(m0, m1), fminf(m2, m3));
+                    m0 = m1 = m2 = m3 = INFINITY;
                     while (cur < O - 1 && rb * RBK >= seg[cur + 1]) ++cur;
                 }
             }
@@ -181,24 +235,25 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
             tc_fence_after();
             const uint32_t t0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)as * RBK;
 #pragma unroll 1
-            for (int c0 = 0; c0 < RBK; c0 += 32) {
-                float v[32];
+            for (int c0 = 0; c0 < RBK; c0 += 64) {
+                float v[64];                                      // two tensor-memory loads in flight per wait
                 tmem_ld32(t0 + c0, v);
+                tmem_ld32(t0 + c0 + 32, v + 32);
                 tmem_ld_wait();
                 if (MODE == 0) {
                     const float4* rr = reinterpret_cast<const float4*>(r2 + (size_t)rb * RBK + c0);
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
+                    for (int j4 = 0; j4 < 16; ++j4) {
                         float4 r4 = __ldg(rr + j4);
-                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 0], qq + r4.x));   // (|q|^2+|r|^2) - 2 q.r  (matching.py:45)
-                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 1], qq + r4.y));
-                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 2], qq + r4.z));
-                        m = fminf(m, fmaf(-2.0f, v[j4 * 4 + 3], qq + r4.w));
+                        m0 = fminf(m0, fmaf(-2.0f, v[j4 * 4 + 0], qq + r4.x));   // (|q|^2+|r|^2) - 2 q.r  (matching.py:45)
+                        m1 = fminf(m1, fmaf(-2.0f, v[j4 * 4 + 1], qq + r4.y));
+                        m2 = fminf(m2, fmaf(-2.0f, v[j4 * 4 + 2], qq + r4.z));
+                        m3 = fminf(m3, fmaf(-2.0f, v[j4 * 4 + 3], qq + r4.w));
                     }
                 } else {
                     float* dst = C + (size_t)qi * ldc + (size_t)rb * RBK + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 64; ++j) dst[j] = v[j];
                 }
             }
             tc_fence_before();
@@ -206,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
             as ^= 1;
             if (as == 0) aphase ^= 1u;
         }
-        if (MODE == 0 && rb1 > rb0 && qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = m;
+        if (MODE == 0 && rb1 > rb0 && qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = fminf(fminf(m0, m1), fminf(m2, m3));
     }
     tc_fence_before();
     __syncthreads();
@@ -308,15 +363,23 @@ extern "C" int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int 
     return launch_status("aoc_pack_tc_image_f32");
 }
 
+namespace aoc {
+int g_match_f16 = 1;     // aoc_set_option("match_f16", 0/1): split-fp16 operands in the global matching contraction
+}
+
 static int pack_centered(const float* x, long long rows, int RB, const float* center, const float* valid_r2, void* out,
-                         cudaStream_t stream) {
-    int ks = TC_KS;
+                         bool f16, cudaStream_t stream) {
+    int ks = f16 ? MatchFmt<true>::KS : MatchFmt<false>::KS;
     long long rows_padded = (rows + RB - 1) / RB * RB;
     long long total = rows_padded * ks * 2;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, 100, 100, RB, ks, rows_padded, (uint8_t*)out, center,
-                                                     valid_r2);
+    if (f16)
+        pack_tc_image_f16_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, 100, 100, RB, ks, rows_padded, (uint8_t*)out,
+                                                             center, valid_r2);
+    else
+        pack_tc_image_kernel<<<blocks, 256, 0, stream>>>(x, (int)rows, 100, 100, RB, ks, rows_padded, (uint8_t*)out,
+                                                         center, valid_r2);
     return launch_status("aoc_global_match_tc(pack)");
 }
 
@@ -353,11 +416,12 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
     int nb = cdiv(HW, MU_SLAB);
     col_sum_partial_kernel<<<nb, 256, 0, stream>>>(q, HW, MU_SLAB, part);
     col_mean_final_kernel<<<1, 128, 0, stream>>>(part, nb, HW, mu);
-    int rc = pack_centered(q, HW, QB, mu, nullptr, Qimg, stream);
+    const bool f16 = g_match_f16 != 0;      // (the fp16 images are smaller: the TF32-sized workspace layout is kept)
+    int rc = pack_centered(q, HW, QB, mu, nullptr, Qimg, f16, stream);
     if (rc) return rc;
     centered_sqnorm_kernel<<<cdiv((long long)HW * 32, 256), 256, 0, stream>>>(q, HW, mu, nullptr, q2);
     if (nrb > 0) {
-        rc = pack_centered(S, rows_padded, RBK, mu, r2, Simg, stream);
+        rc = pack_centered(S, rows_padded, RBK, mu, r2, Simg, f16, stream);
         if (rc) return rc;
         centered_sqnorm_kernel<<<cdiv((long long)rows_padded * 32, 256), 256, 0, stream>>>(S, rows_padded, mu, r2, r2c);
     }
@@ -366,12 +430,17 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
     fill_f32_kernel<<<cdiv(n * nsplit, 1024), 256, 0, stream>>>(mins, INFINITY, n * nsplit);
     if (nrb > 0) {
         if (!g_attr0) {
-            cudaFuncSetAttribute(match_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
+            cudaFuncSetAttribute(match_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<false>::SMEM);
+            cudaFuncSetAttribute(match_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<true>::SMEM);
             g_attr0 = true;
         }
         dim3 grid(nqt, nsplit);
-        match_tc_kernel<0><<<grid, 256, SMEM_MATCH, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb, nsplit, mins,
-                                                             nullptr, 0, LBO_BYTES, SBO_BYTES);
+        if (f16)
+            match_tc_kernel<0, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb, nsplit,
+                                                                                 mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
+        else
+            match_tc_kernel<0, false><<<grid, 256, MatchFmt<false>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb,
+                                                                                   nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
         if (nsplit > 1) min_over_splits_kernel<<<cdiv(n, 256), 256, 0, stream>>>(mins, n, nsplit);
     }
     rc = aoc_global_match_finalize_f32(mins, meta_dev, bias, HW, O, out, stream);
@@ -394,12 +463,12 @@ extern "C" int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, in
     rc = aoc_pack_tc_image_f32(B, N, K, K, RBK, TC_K, Bi, stream);
     if (rc) return rc;
     if (!g_attr1) {
-        cudaFuncSetAttribute(match_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
+        cudaFuncSetAttribute(match_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
         g_attr1 = true;
     }
     dim3 grid(M / QB, 1);
     uint32_t lbo = variant == 1 ? SBO_BYTES : LBO_BYTES, sbo = variant == 1 ? LBO_BYTES : SBO_BYTES;
-    match_tc_kernel<1><<<grid, 256, SMEM_MATCH, stream>>>(Ai, Bi, nullptr, nullptr, nullptr, 1, M, N / RBK, 1, nullptr, C,
+    match_tc_kernel<1, false><<<grid, 256, SMEM_MATCH, stream>>>(Ai, Bi, nullptr, nullptr, nullptr, 1, M, N / RBK, 1, nullptr, C,
                                                          N, lbo, sbo);
     return launch_status("aoc_gemm_tf32x3_test");
 }

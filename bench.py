@@ -268,8 +268,8 @@ def main():
                           "%d timed predicted frames, memory bank +1 frame every %d, one independent clip per GPU"
                           % (H, W, K_OBJ, args.warmup, args.steps, MEM_EVERY),
               "l2": "no flush: per-step working set (>300 MB of activations + bank) exceeds the 126 MB L2",
-              "precision": "fp32 I/O; fp32-faithful tensor-core kernels: convolution = split-fp16 operand pairs (22 mantissa bits, "
-                           "3 kind::f16 MMAs per product), matching = 3xTF32; fp32 accumulate"}
+              "precision": "fp32 I/O; fp32-faithful tensor-core kernels: convolution and matching contract split-fp16 operand pairs "
+                           "(22 mantissa bits, 3 kind::f16 MMAs per fp32 product), fp32 accumulate"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -338,9 +338,9 @@ def main():
                  "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 kind::f16 MMAs per product (hi*hi, lo*hi, "
                  "hi*lo), so its hardware ceiling is peak/3; traffic = DRAM bytes of the largest layer's launch (decoder conv1, "
                  "algorithmic 277 MB) from profiles/r1_conv2_dec_conv1_f16_ncu_full.txt", 255374592),
-                ("match", "match_tc_kernel (tcgen05 global matching, 3xTF32)", 6.0,
-                 "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 TF32 MMAs per product at half the bf16 "
-                 "rate, so its hardware ceiling is peak/6", None)):
+                ("match", "match_tc_kernel (tcgen05 global matching with fused segmented-min epilogue, split-fp16 operands)", 3.0,
+                 "achieved counts algorithmic fp32 FLOPs once (2 x queries x padded bank rows x 100); the kernel issues 3 "
+                 "kind::f16 MMAs per product, so its hardware ceiling is peak/3", None)):
             if key in prof:
                 p = prof[key]
                 ach = p["flop"] / (p["ms"] * 1e-3) / 1e12
