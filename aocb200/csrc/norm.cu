@@ -137,7 +137,13 @@ __global__ void channel_stats_final(const double* __restrict__ part, int S, int 
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C2) return;
     double a = 0.0;
-    for (int s = 0; s < S; ++s) a += part[((size_t)(n * S + s)) * C2 + c];
+    for (int s = 0; s < S; s += 4) {                     // four slabs per iteration: independent loads, added in slab order
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = s + u < S ? part[((size_t)(n * S + s + u)) * C2 + c] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a += v[u];
+    }
     stats[(size_t)n * C2 + c] = a;
 }
 
@@ -286,7 +292,17 @@ __global__ void __launch_bounds__(256) gn_coeffs_tiles_kernel(const float* __res
     if (tl < lanes) {
         const int stat = it / cpg, ch = it - stat * cpg;
         const float* p = part + ((size_t)n * tiles_per_image * 2 + stat) * C + g * cpg + ch;
-        for (int t = tl; t < tiles_per_image; t += lanes) acc += (double)__ldg(p + (size_t)t * 2 * C);
+        // four tiles per iteration: independent loads in flight, added in tile order
+        for (int t = tl; t < tiles_per_image; t += 4 * lanes) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int tt = t + u * lanes;
+                v[u] = tt < tiles_per_image ? __ldg(p + (size_t)tt * 2 * C) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc += (double)v[u];
+        }
     }
     sm[threadIdx.x] = acc;
     __syncthreads();

@@ -136,6 +136,11 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
     st = Stepper(model, frames, first, K_OBJ, device, host_io)
     for _ in range(warmup):
         st.step()
+    # a generation-2 pass of Python's cyclic collector over the process heap (weights, graphs, fixtures) is a 10-40 ms
+    # host pause; the per-frame path creates no reference cycles worth collecting inside K steps
+    import gc
+    gc.collect()
+    gc.disable()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -152,6 +157,7 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    gc.enable()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     if dist:

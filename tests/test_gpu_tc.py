@@ -155,8 +155,10 @@ def test_conv_tc_chunking(eng):
     assert e_short < 0.2 * e_long
 
 
-def test_global_match_tc_vs_simt(eng):
+@pytest.mark.parametrize("f16", [1, 0], ids=["split-fp16", "3xTF32"])
+def test_global_match_tc_vs_simt(eng, f16):
     from test_gpu_ops import _rand_scene
+    eng.L.set_option(b"match_f16", f16)
     for seed, h, w, K, F_, absent in ((1, 25, 33, 3, 2, None), (2, 61, 107, 5, 2, 4), (3, 33, 37, 1, 3, None)):
         embs, masks, _ = _rand_scene(seed, h, w, K, F_, absent)
         outs = {}
@@ -172,3 +174,4 @@ def test_global_match_tc_vs_simt(eng):
         eng.keep_debug = False
         eng.tc_match = True
         report("global match tcgen05 vs simt (seed %d)" % seed, outs[True], outs[False], 5e-6)
+    eng.L.set_option(b"match_f16", 1)

@@ -19,9 +19,15 @@ def main():
     model = get_module()(None, None)
     model.load_state_dict(synthetic_state_dict(1234))
     model = model.cuda(0).eval()
-    for rep in range(2):
+    smi = None
+    if "smi" in sys.argv:                                   # with bench.py's nvidia-smi clock sampler polling alongside
+        from bench import ClockSampler
+        smi = ClockSampler(0)
+        smi.start()
+    for rep in range(3 if smi else 2):
         np.random.seed(1000)
-        st = Stepper(model, frames, first, 5, dev, False)
+        e2e = len(sys.argv) > 1 and sys.argv[1] == "e2e"      # host buffers + a stream sync per step, as in bench.py's e2e arm
+        st = Stepper(model, frames, first, 5, dev, e2e)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         host = []
         torch.cuda.synchronize()
@@ -36,6 +42,8 @@ def main():
         print("pass %d: total %.1f ms, %.2f ms/step" % (rep, sum(dv), sum(dv) / n))
         print("  device ms:", " ".join("%.1f" % v for v in dv))
         print("  host ms:  ", " ".join("%.1f" % v for v in host))
+    if smi:
+        print(smi.stop())
 
 
 if __name__ == "__main__":
