@@ -199,19 +199,20 @@ __global__ void __launch_bounds__(256) kmeans_step_kernel(const float* __restric
     }
 }
 
-// Second stage, one block per (cluster j, object o): warp w sums the slabs b = w, w+8, ... (lanes over channels,
-// 128-bit loads), the 8 warps are combined in a fixed order in double precision.
+// Second stage, one block per (cluster j, object o): warp w sums the slabs b = w, w+32, ... (lanes over channels,
+// 128-bit loads), the 32 warps are combined in a fixed order in double precision.
 // MODE 0: Lloyd update (cent[j] = sum/cnt, empty keeps previous).  MODE 1: write centroid_avg + validity.
 // P: [O][AOC_PROXY_SLOTS][EMB], pvalid: [O][AOC_PROXY_SLOTS]
+constexpr int KR_WARPS = 32;     // the slab loop is one L2 round trip per iteration: 32 warps keep it to a handful
 template <int MODE>
-__global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restrict__ part,
+__global__ void __launch_bounds__(KR_WARPS * 32) kmeans_reduce_kernel(const float* __restrict__ part,
                                                              const int* __restrict__ pcnt,
                                                              const int* __restrict__ meta,
                                                              const int* __restrict__ kk, int nb_max,
                                                              int rows_per_block, float* __restrict__ cent,
                                                              float* __restrict__ P, int* __restrict__ pvalid) {
-    __shared__ double sm[8][EMB];
-    __shared__ int sn[8];
+    __shared__ double sm[KR_WARPS][EMB];
+    __shared__ int sn[KR_WARPS];
     const int j = blockIdx.x, o = blockIdx.y;
     const int n_o = meta[o];
     const int k = kk[o];
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int n = 0;
     if (j < k) {
-        for (int b = warp; b < nb; b += 8) {
+        for (int b = warp; b < nb; b += KR_WARPS) {
             const size_t pbase = ((size_t)o * nb_max + b) * KM_K + j;
             if (lane < EMB4) {
                 float4 v = ldg4(part + pbase * EMB + lane * 4);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256) kmeans_reduce_kernel(const float* __restr
     if (c >= EMB) return;
     double s = 0.0;
     long long cntj = 0;
-    for (int w = 0; w < 8; ++w) { s += sm[w][c]; cntj += sn[w]; }
+    for (int w = 0; w < KR_WARPS; ++w) { s += sm[w][c]; cntj += sn[w]; }
     const int i = j * EMB + c;
     if (MODE == 0) {
         if (j < k && cntj > 0) cent[(size_t)o * KM_K * EMB + i] = (float)s / (float)cntj;
@@ -291,10 +292,10 @@ extern "C" int aoc_kmeans_proxies_f32(const float* S, const int* meta, const int
     dim3 gs(nb, O), gr(KM_K, O);
     for (int it = 0; it < iters; ++it) {
         kmeans_step_kernel<true, false><<<gs, 256, KM_SMEM, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
-        kmeans_reduce_kernel<0><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
+        kmeans_reduce_kernel<0><<<gr, KR_WARPS * 32, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
     }
     // centroid_avg: same labels, rows taken from the all-object bank in natural order (matching.py:589)
     kmeans_step_kernel<false, true><<<gs, 256, KM_SMEM, stream>>>(S, meta, kk, cent, nat2sorted, labels, part, pcnt, nb);
-    kmeans_reduce_kernel<1><<<gr, 256, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
+    kmeans_reduce_kernel<1><<<gr, KR_WARPS * 32, 0, stream>>>(part, pcnt, meta, kk, nb, rpb, cent, P, pvalid);
     return launch_status("aoc_kmeans_proxies_f32");
 }
