@@ -5,16 +5,20 @@
 // decoding_module.py:162-190,228-240), with the per-(sample, channel) affine that precedes them in the reference
 // (GroupNorm apply + ReLU, GCT / IA gate) fused into the operand path.
 //
-// Data flow of one CTA (128 output pixels x TN output channels, K consumed in stages of 16 input channels of one tap):
-//   warp 12  TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][32 channels] (zero fill = conv padding,
-//            element strides = conv stride, 128B swizzle) into a 4-deep ring; one box feeds two operand stages
-//   warps 0-3  transform (thread = pixel = TMEM lane): raw -> (optional a*x+b, ReLU, padding mask) -> 3xTF32 split
-//            hi = rna(x), lo = rna(x - hi) -> tcgen05.st into a 4-deep operand ring in TENSOR memory
-//   warp 13  TMA bulk copies of the pre-split weight image into the shared-memory operand ring
-//   warp 14  warp-uniform loop, one elected lane issues tcgen05.mma kind::tf32 with the A operand from TMEM:
-//            hi*hi -> MAIN accumulator, lo*hi + hi*lo -> CORR accumulator
-//   warps 4-11 drain: every `chunk` stages the MAIN accumulator (double buffered in TMEM) is read with tcgen05.ld and
-//            added to fp32 registers with round-to-nearest; epilogue adds CORR, bias, residual, ReLU; 128-bit stores.
+// Data flow of one persistent CTA (work items = 128 output pixels x TN output channels [x a K slice]; K consumed in
+// stages of 16 input channels of one filter tap; 20 warps, register file re-partitioned per role with setmaxnreg):
+//   warp 16    TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][32 channels] (zero fill = conv padding,
+//              element strides = conv stride, 128B swizzle) into a 6-deep ring; one box feeds two operand stages
+//   warps 0-7  transform, two sets of four owning alternate stages (thread = pixel = TMEM lane): raw -> (optional a*x+b,
+//              ReLU, padding mask) -> operand split -> tcgen05.st into an operand ring in TENSOR memory.  Operand formats:
+//              split-fp16 (default): hi = fp16(x), lo = fp16((x - hi) * 2^11), one K = 16 kind::f16 MMA per term;
+//              3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi), two K = 8 kind::tf32 MMAs per term
+//   warp 17    TMA bulk copies of the pre-split weight image into the shared-memory operand ring
+//   warps 18/19  warp-uniform loops, one elected lane issues tcgen05.mma with the A operand from TMEM:
+//              hi*hi -> MAIN accumulator (warp 18), lo*hi + hi*lo -> CORR accumulator (warp 19)
+//   warps 8-15 drain: every `chunk` stages the MAIN accumulator (double buffered in TMEM) is read with tcgen05.ld and
+//              added to fp32 registers with round-to-nearest; the epilogue adds CORR (x 2^-11 for split-fp16), transposes
+//              through shared memory, applies bias, residual, ReLU, writes 128-byte lines and per-tile statistics.
 // Shared memory only carries the raw patch and the weights: with both operands in shared memory the 128 B/clk port was
 // the limit (measured 821 us vs 764 us on the largest layer), and the per-MMA operand set-up must come from uniform
 // registers (a divergent single-thread issue loop cost ~14 instructions per MMA: 764 us -> 509 us once warp-uniform).
