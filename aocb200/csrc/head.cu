@@ -79,6 +79,54 @@ __global__ void upsample_softmax_kernel(const float* __restrict__ logits, float*
     if (label) label[i] = (uint8_t)am;
 }
 
+// The eval loop's per-frame label bookkeeping fused behind the upsample + softmax (eval_manager_mm.py:252-270 label
+// filter, :318-320 argmax, :339-349 uncertainty filter; shannon_entropy.py:10-13):
+//   probs[o] = softmax_o(upsampled logits) for labels seen in a ground-truth frame so far, 0 otherwise
+//   label    = argmax_o probs (lowest index wins ties, as torch.argmax)
+//   ent      = -sum_{o seen} p_o * log(p_o + 1e-6)
+//   conf     = ent > unc_ratio ? 125 : label      (125 = "uncertain": matches no object slot in the memory bank)
+// exist: device word, bit o set <=> label o has been seen (null = all); a device word so that a captured graph follows
+// the caller's set without re-capture.
+__global__ void upsample_softmax_label_kernel(const float* __restrict__ logits, float* __restrict__ probs,
+                                              uint8_t* __restrict__ label, uint8_t* __restrict__ conf,
+                                              float* __restrict__ entropy, const int* __restrict__ exist,
+                                              float unc_ratio, int O, int h, int w, int H, int W, float sh, float sw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W) return;
+    const unsigned ex = exist ? (unsigned)__ldg(exist) : 0xffffffffu;
+    int yo = i / W, xo = i - yo * W;
+    float ry = sh * (float)yo, rx = sw * (float)xo;
+    int y0 = min((int)ry, h - 1), x0 = min((int)rx, w - 1);
+    int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    float ly1 = fminf(fmaxf(ry - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(rx - (float)x0, 0.f), 1.f);
+    float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    float v[AOC_MAX_OBJECTS];
+    float mx = -INFINITY;
+    for (int o = 0; o < O; ++o) {
+        const float* L = logits + (size_t)o * h * w;
+        float t = ly0 * (lx0 * __ldg(L + y0 * w + x0) + lx1 * __ldg(L + y0 * w + x1)) +
+                  ly1 * (lx0 * __ldg(L + y1 * w + x0) + lx1 * __ldg(L + y1 * w + x1));
+        v[o] = t;
+        mx = fmaxf(mx, t);
+    }
+    float s = 0.f;
+    for (int o = 0; o < O; ++o) { v[o] = expf(v[o] - mx); s += v[o]; }
+    float inv = 1.0f / s;
+    float best = -1.f, ent = 0.f;
+    int am = 0;
+    for (int o = 0; o < O; ++o) {
+        const bool seen = (ex >> o) & 1u;
+        const float pr = seen ? v[o] * inv : 0.f;
+        probs[(size_t)o * H * W + i] = pr;
+        if (pr > best) { best = pr; am = o; }
+        if (seen) ent += pr * logf(pr + 1e-6f);
+    }
+    ent = -ent;
+    label[i] = (uint8_t)am;
+    if (conf) conf[i] = ent > unc_ratio ? (uint8_t)125 : (uint8_t)am;
+    if (entropy) entropy[i] = ent;
+}
+
 }  // namespace aoc
 
 using namespace aoc;
@@ -104,4 +152,16 @@ extern "C" int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8
     upsample_softmax_kernel<<<cdiv((long long)H * W, 256), 256, 0, stream>>>(logits, probs, label, O, h, w, H, W, sh,
                                                                            sw);
     return launch_status("aoc_upsample_softmax_f32");
+}
+
+extern "C" int aoc_upsample_softmax_label_f32(const float* logits, float* probs, uint8_t* label, uint8_t* conf_label,
+                                              float* entropy, const int* exist_bits, float unc_ratio, int O, int h,
+                                              int w, int H, int W, cudaStream_t stream) {
+    AOC_CHECK_ARG(logits && probs && label, "null pointer");
+    AOC_CHECK_ARG(O >= 1 && O <= AOC_MAX_OBJECTS && h > 0 && w > 0 && H > 0 && W > 0, "bad dims");
+    float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
+    float sw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+    upsample_softmax_label_kernel<<<cdiv((long long)H * W, 256), 256, 0, stream>>>(
+        logits, probs, label, conf_label, entropy, exist_bits, unc_ratio, O, h, w, H, W, sh, sw);
+    return launch_status("aoc_upsample_softmax_label_f32");
 }

@@ -184,6 +184,11 @@ class Engine:
         self._gt_cache = (None, 0)
         self._ws_keep = []
         self._ws = {}
+        # eval-loop label bookkeeping on the device: bit o of the word = label o was seen in a
+        # ground-truth frame (eval_manager_mm.py:252-270); entropy threshold of the confident mask (:339-349)
+        self._exist = torch.full((1,), -1, dtype=torch.int32, device=self.dev)
+        self.unc_ratio = 1.0
+        self.last_logits = self.last_label = self.last_conf_label = None
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -770,11 +775,25 @@ class Engine:
             self._gt_cache = (key, int(gt_ids[0]))
         return self._gt_cache[1]
 
+    def set_seen_labels(self, labels=None):
+        """Labels that appeared in a ground-truth frame of this sequence so far (`label_all_list`,
+        eval_manager_mm.py:262-265); None = every slot.  Probabilities of the other slots come back as zeros."""
+        bits = -1
+        if labels is not None:
+            bits = 0
+            for v in labels:
+                if 0 <= int(v) < MAXO:
+                    bits |= 1 << int(v)
+            bits -= (1 << 32) if bits >= (1 << 31) else 0
+        self._exist.copy_(torch.tensor([bits], dtype=torch.int32))    # pageable source: staged before the call returns
+
     def _upsample_softmax(self, logits, O, h, w, H, W):
         probs = torch.empty((1, O, H, W), dtype=torch.float32, device=self.dev)
         label = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
-        self.L.upsample_softmax_f32(logits.data_ptr(), probs.data_ptr(), label.data_ptr(), O, h, w, H, W, self.stream)
-        return probs, label
+        conf = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
+        self.L.upsample_softmax_label_f32(logits.data_ptr(), probs.data_ptr(), label.data_ptr(), conf.data_ptr(), None,
+                                          self._exist.data_ptr(), float(self.unc_ratio), O, h, w, H, W, self.stream)
+        return probs, label, conf
 
     def forward_for_eval(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
                          pred_size, gt_ids):
@@ -790,9 +809,9 @@ class Engine:
         x, head, _ = self.match_features(ref_embeddings, ref_masks, prev_embedding, prev_mask, emb, K)
         logits, mem = self.calibration_decoding(x, head, list(memory_prev_list[0]), low)
         H, W = int(pred_size[0]), int(pred_size[1])
-        probs, label = self._upsample_softmax(logits, O, emb.H, emb.W, H, W)
+        probs, label, conf = self._upsample_softmax(logits, O, emb.H, emb.W, H, W)
         self.last_logits = logits.view(1, O, emb.H, emb.W)
-        self.last_label = label
+        self.last_label, self.last_conf_label = label, conf
         return probs, emb_out, [[mem[0].nchw(), mem[1].nchw()]]
 
     # ------------------------------------------------------------------ CUDA-graph schedule
@@ -899,8 +918,8 @@ class Engine:
             x = self._match_back(emb, st["g"], st["P"], st["pvalid"], st["head"], st["prev_e"], st["prev_ids"], O)
             logits, mem = self.calibration_decoding(x, st["head"], [st["mem"][0].nchw() if has[0] else None,
                                                                     st["mem"][1].nchw() if has[1] else None], low)
-            probs, label = self._upsample_softmax(logits, O, h, w, Hp, Wp)
-            return logits, mem, probs, label
+            probs, label, conf = self._upsample_softmax(logits, O, h, w, Hp, Wp)
+            return logits, mem, probs, label, conf
 
         # ---- segment F: bank-dependent (global matching, k-means proxies, bank heads)
         if ix["rows"] == 0:
@@ -919,7 +938,7 @@ class Engine:
                 st["segF"] = segF
             segF["graph"].replay()
         # ---- segment C: everything after the bank
-        keyC = (Hp, Wp, has[0], has[1], id(emb))
+        keyC = (Hp, Wp, has[0], has[1], id(emb), float(self.unc_ratio))
         segC = st["segC"].get(keyC)
         if segC is None:
             back()                                           # warm-up
@@ -927,8 +946,8 @@ class Engine:
             segC = dict(graph=gC, out=out)
             st["segC"][keyC] = segC
         segC["graph"].replay()
-        logits, mem, probs, label = segC["out"]
+        logits, mem, probs, label, conf = segC["out"]
         self.last_logits = logits.view(1, O, h, w)
-        self.last_label = label
+        self.last_label, self.last_conf_label = label, conf      # static buffers of the graph: clone to keep
         cl = torch.channels_last
         return probs.clone(), emb_out, [[mem[0].nchw().clone(memory_format=cl), mem[1].nchw().clone(memory_format=cl)]]

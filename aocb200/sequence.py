@@ -16,9 +16,11 @@ def shannon_entropy(probs):
 
 
 def run_sequence(model, frames, first_label, num_objects, mem_every=5, unc_ratio=1.0,
-                 device=None, on_frame=None, keep_probs=False):
+                 device=None, on_frame=None, keep_probs=False, later_labels=None):
     """frames [T,3,H,W] (normalised), first_label [H,W] ints 0..K.  Returns list of predicted label
-    maps [H,W] (int64) for frames 1..T-1 (and the per-frame probabilities when keep_probs)."""
+    maps [H,W] (int64) for frames 1..T-1 (and the per-frame probabilities when keep_probs).
+    later_labels: {t: [H,W] label map} ground truth given at later frames (YouTube-VOS: objects that
+    enter after the first frame, eval_manager_mm.py:288-292,:321-349)."""
     T, _, H, W = frames.shape
     dev = device if device is not None else frames.device
     gt_ids = torch.tensor([num_objects], device=dev)
@@ -46,8 +48,18 @@ def run_sequence(model, frames, first_label, num_objects, mem_every=5, unc_ratio
         else:
             probs_exist = probs
         pred = torch.argmax(probs[0], dim=0)                                   # :318-320
+        join = later_labels.get(t) if later_labels else None
+        if join is not None:                                                   # :321-349 new objects join here
+            join = join.to(pred.device).long()
+            seen |= set(int(v) for v in torch.unique(join).tolist())           # :262-265
+            keep = (join == 0).long()
+            pred = pred * keep + join * (1 - keep)
+            unc = shannon_entropy(probs_exist)[0, 0] * keep                    # (join < 0) is empty for label maps
+            region = (unc > unc_ratio).long()
+            conf = (pred * (1 - region) + 125 * region).view(1, 1, H, W)
+            ref_emb.append(emb); ref_mask_conf.append(conf)                    # :296-297,:349
         cur = pred.view(1, 1, H, W)
-        if mem_every > -1 and t % mem_every == 0:                              # :309-312,:356-361
+        if join is None and mem_every > -1 and t % mem_every == 0:             # :309-312,:356-361
             unc = shannon_entropy(probs_exist)[0, 0]
             region = (unc > unc_ratio).long()
             conf = (pred * (1 - region) + 125 * region).view(1, 1, H, W)
@@ -59,3 +71,68 @@ def run_sequence(model, frames, first_label, num_objects, mem_every=5, unc_ratio
         if on_frame is not None:
             on_frame(t, probs, pred)
     return (preds, probs_out) if keep_probs else preds
+
+
+class DeviceSequence:
+    """The same bookkeeping with every piece of per-sequence state resident on the GPU: label maps
+    are uint8 device tensors, the label-existence filter (eval_manager_mm.py:252-270), the argmax (:318-320) and the
+    entropy -> label-125 "confident" mask (:339-349, shannon_entropy.py:10-13) come out of the engine's fused
+    upsample + softmax kernel (`aoc_upsample_softmax_label_f32`), so a predicted frame adds no torch kernels and
+    no host read-back to `forward_for_eval`.  CUDA engine only (`model.engine()`); no fallback."""
+
+    def __init__(self, model, num_objects, mem_every=5, unc_ratio=1.0, device=None):
+        self.m, self.eng = model, model.engine()
+        self.dev = device if device is not None else self.eng.dev
+        self.K, self.mem_every = int(num_objects), int(mem_every)
+        self.eng.unc_ratio = float(unc_ratio)
+        self.gt_ids = torch.tensor([self.K], device=self.dev)
+        self.ref_e, self.ref_m = [], []
+        self.prev_e = self.prev_m = None
+        self.memory = [[None, None]]
+        self.seen = set()
+        self.t = -1
+
+    def _see(self, label):
+        new = set(int(v) for v in torch.unique(label).tolist()) - self.seen      # GT frames only: one small read-back
+        if new:
+            self.seen |= new
+            self.eng.set_seen_labels(self.seen)
+
+    def step(self, img, gt_label=None):
+        """img [1,3,H,W] normalised frame (device or pinned host); gt_label [H,W] ints if this frame carries ground
+        truth (always the first).  Returns the frame's label map, uint8 [H,W] on the device (the GT itself for t = 0)."""
+        self.t += 1
+        t = self.t
+        H, W = int(img.shape[-2]), int(img.shape[-1])
+        img = img.to(self.dev, non_blocking=True)
+        if gt_label is not None:
+            gt_label = gt_label.to(self.dev).to(torch.uint8).view(H, W)
+            if t == 0:
+                self._see(gt_label)
+        probs, emb, self.memory = self.m.forward_for_eval(self.memory, self.ref_e, self.ref_m, self.prev_e, self.prev_m,
+                                                          img, pred_size=[H, W], gt_ids=self.gt_ids)
+        if t == 0:
+            assert gt_label is not None, "the first frame carries the ground-truth label"
+            lab = gt_label.view(1, 1, H, W)
+            self.ref_e.append(emb); self.ref_m.append(lab)
+            self.prev_e, self.prev_m = emb, lab
+            return gt_label
+        self.probs = probs
+        pred = self.eng.last_label.clone()
+        if gt_label is not None:                                               # new objects join (:321-349)
+            self._see(gt_label)
+            conf = torch.where(gt_label != 0, gt_label, self.eng.last_conf_label)
+            pred = torch.where(gt_label != 0, gt_label, pred)
+            self.ref_e.append(emb); self.ref_m.append(conf.view(1, 1, H, W))
+        elif self.mem_every > -1 and t % self.mem_every == 0:
+            self.ref_e.append(emb); self.ref_m.append(self.eng.last_conf_label.clone().view(1, 1, H, W))
+        self.prev_e, self.prev_m = emb, pred.view(1, 1, H, W)
+        return pred
+
+
+def run_sequence_device(model, frames, first_label, num_objects, mem_every=5, unc_ratio=1.0, later_labels=None):
+    """run_sequence() on a DeviceSequence: same arguments, label maps returned as uint8 device tensors."""
+    seq = DeviceSequence(model, num_objects, mem_every, unc_ratio)
+    seq.step(frames[0:1], first_label)
+    return [seq.step(frames[t:t + 1], later_labels.get(t) if later_labels else None)
+            for t in range(1, frames.shape[0])]

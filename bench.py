@@ -89,8 +89,6 @@ class Stepper:
     """The eval loop of aocb200/sequence.py unrolled into explicit steps (so that exactly K of them can be timed)."""
 
     def __init__(self, model, frames, first_label, K, device, host_io):
-        from aocb200.sequence import shannon_entropy
-        self.ent = shannon_entropy
         self.m, self.K, self.dev, self.host_io = model, K, device, host_io
         self.T, _, self.H, self.W = frames.shape
         self.frames = frames.pin_memory() if host_io else frames.to(device)
@@ -116,16 +114,15 @@ class Stepper:
             self.h2d += img.numel() * 4
         probs, emb, self.memory = self.m.forward_for_eval(self.memory, self.ref_e, self.ref_m, self.prev_e, self.prev_m,
                                                           img, pred_size=[self.H, self.W], gt_ids=self.gt_ids)
-        pred = torch.argmax(probs[0], dim=0)
-        cur = pred.view(1, 1, self.H, self.W)
+        # label bookkeeping of the eval loop (eval_manager_mm.py:252-361) straight from the fused upsample + softmax
+        # kernel: argmax and the entropy -> label-125 "confident" mask are uint8 device maps, no torch kernels
+        eng = self.m.engine()
+        pred = eng.last_label.clone()
         if t % MEM_EVERY == 0:                                   # eval_manager_mm.py:309-312,:339-361
-            unc = self.ent(probs)[0, 0]
-            region = (unc > 1.0).long()
-            conf = (pred * (1 - region) + 125 * region).view(1, 1, self.H, self.W)
-            self.ref_e.append(emb); self.ref_m.append(conf)
-        self.prev_e, self.prev_m = emb, cur
+            self.ref_e.append(emb); self.ref_m.append(eng.last_conf_label.clone().view(1, 1, self.H, self.W))
+        self.prev_e, self.prev_m = emb, pred.view(1, 1, self.H, self.W)
         if self.host_io:
-            self.out_host.copy_(pred.to(torch.uint8), non_blocking=True)
+            self.out_host.copy_(pred, non_blocking=True)
             self.d2h += self.out_host.numel()
             torch.cuda.current_stream().synchronize()            # the caller consumes the mask of this frame
         return pred

@@ -203,6 +203,15 @@ int aoc_dyn_logits_f32(const float* x, const float* wfg, const float* wbg, float
                        int HW, int C, int ldx, cudaStream_t stream);
 int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8_t* label, int O, int h, int w, int H, int W,
                              cudaStream_t stream);
+/* The same upsample + softmax with the eval loop's per-frame label bookkeeping fused behind it (SURVEY 8f rows 1-2;
+ * eval_manager_mm.py:252-270 "delete the label that hasn't existed in the GT label", :318-320 argmax, :339-349
+ * uncertainty region filter; layers/shannon_entropy.py:10-13).  exist_bits: device int32 word, bit o set <=> label o
+ * was seen in a ground-truth frame so far (NULL = every slot); probs[o] of an unseen slot is 0; label = argmax of the
+ * filtered probs (uint8, lowest index on ties); conf_label (optional) = 125 where the entropy over the seen slots
+ * exceeds unc_ratio, else label -- the "confident" mask the memory bank stores; entropy (optional) [H][W] floats. */
+int aoc_upsample_softmax_label_f32(const float* logits, float* probs, uint8_t* label, uint8_t* conf_label,
+                                   float* entropy, const int* exist_bits, float unc_ratio, int O, int h, int w, int H,
+                                   int W, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- tcgen05 self-test (umma_gemm.cu) */
 /* C[M][N] = A[M][K] * B[N][K]^T through the same tcgen05 pipeline as aoc_global_match_tc (M%128==0, N%256==0,
