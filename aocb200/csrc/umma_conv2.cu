@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     // global memory first executes griddepcontrol.wait (= the previous grid has completed and its writes are visible).
     asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 17 && lane == 0) {
-        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 8); }
+        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
         for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1 + NCI); mbar_init(B_FULL(s), 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), NCI);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         int sr = 0, so = 0;
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
-        int gi = 0;                                                          // running operand-stage index (parity = owner)
+        int bi = 0;                                                          // running raw-box index (parity = owner set)
         int pend = -1;                                                       // operand slot stored but not yet published
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
@@ -245,96 +245,110 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 tr = tap / p.kw; ts = tap - tr * p.kw;
                 ok = (unsigned)(hb + tr * p.dil) < (unsigned)p.H && (unsigned)(wb + ts * p.dil) < (unsigned)p.W;
             }
-            for (int it = tl.it0; it < tl.it1; ++it, ++gi) {
-                // both sets walk every raw stage (so neither can lap the producer); only the owner reads its half
-                if ((cc & 1) == 0) mbar_wait(RAW_FULL(sr), pr);
-                if ((gi & 1) == g) {
-                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(1, it);
-                    float v[16];
+            // A set owns whole raw boxes (32 channels = two operand stages, one for an odd tail), alternating with the
+            // other set; the box's RAW_FULL / RAW_EMPTY barriers are touched by the owner only (RAW_EMPTY counts its four
+            // warps), so a set spends a handful of counter updates on a box it does not own.
+            for (int rb = tl.r0; rb < tl.r1; ++rb, ++bi) {
+                const int nst = (cc + 1 < p.ncc) ? 2 : 1;
+                if ((bi & 1) == g) {
+                    mbar_wait(RAW_FULL(sr), pr);
                     const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
-                    const uint32_t c8 = (uint32_t)(cc & 1) * 4u;
+                    int so_s = so;
+                    uint32_t po_s = po;
+#pragma unroll 1
+                    for (int hs = 0; hs < nst; ++hs) {
+                        const int ccs = cc + hs;
+                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(1, tap * p.ncc + ccs);
+                        float v[16];
+                        const uint32_t c8 = (uint32_t)hs * 4u;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                     : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
-                                     : "r"(rawb + (((c8 + j) ^ sw) << 4)));
-                    if (affine) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 a4, b4;
+                        for (int j = 0; j < 4; ++j)
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
-                                         : "r"(tab_s + (uint32_t)((cc * C2_KC + j * 4) * 4)));
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
-                                         : "r"(tab_s + (uint32_t)((C2_MAX_AFFINE_C + cc * C2_KC + j * 4) * 4)));
-                            v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
-                            v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
-                        }
-                        if (p.in_relu) {
+                                         : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                                         : "r"(rawb + (((c8 + j) ^ sw) << 4)));
+                        if (affine) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-                        }
-                        if (!ok) {
+                            for (int j = 0; j < 4; ++j) {
+                                float4 a4, b4;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                                             : "r"(tab_s + (uint32_t)((ccs * C2_KC + j * 4) * 4)));
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                                             : "r"(tab_s + (uint32_t)((C2_MAX_AFFINE_C + ccs * C2_KC + j * 4) * 4)));
+                                v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
+                                v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
+                            }
+                            if (p.in_relu) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                                for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+                            }
+                            if (!ok) {
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                            }
                         }
+                        float o[Cfg::A_COLS];
+                        if (F16) {
+                            // split-fp16 operand: x = hi + 2^-11 * lo with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22
+                            // mantissa bits like the TF32 pair, but one K = 16 MMA per term instead of two K = 8 ones.
+                            // Columns of the stage: [hi: k0..15, two per column][lo: k0..15]; |x| saturates at the fp16
+                            // range (65504).  hi - x comes from the mixed-precision subtract (one FHADD on the packed
+                            // half, exact in fp32) instead of a half -> float conversion and an FADD.
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                uint32_t h, l;
+                                float d0, d1;
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+                                asm("{\n\t.reg .b16 e0, e1;\n\tmov.b32 {e0, e1}, %2;\n\t"
+                                    "sub.rn.f32.f16 %0, e0, %3;\n\tsub.rn.f32.f16 %1, e1, %4;\n\t}"
+                                    : "=f"(d0), "=f"(d1) : "r"(h), "f"(v[2 * j]), "f"(v[2 * j + 1]));
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d1 * -2048.f), "f"(d0 * -2048.f));
+                                o[j] = __uint_as_float(h);
+                                o[8 + j] = __uint_as_float(l);
+                            }
+                        } else {
+                            // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                float h, l;
+                                split_tf32(v[e], h, l);
+                                o[(e >> 3) * 16 + (e & 7)] = h;
+                                o[(e >> 3) * 16 + 8 + (e & 7)] = l;
+                            }
+                        }
+                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(2, tap * p.ncc + ccs);
+                        // the tensor-memory store of the set's previous stage completes under this stage's ALU work: it
+                        // is waited for and published only now (the MMA side runs stages behind, nothing waits on it)
+                        if (pend >= 0) {
+                            tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(OP_FULL(pend));
+                        }
+                        mbar_wait(OP_EMPTY(so_s), po_s ^ 1u);
+                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, tap * p.ncc + ccs);
+                        tc_fence_after();
+                        if (F16) tmem_st16(a_lane + (uint32_t)(so_s * Cfg::A_COLS), o);
+                        else     tmem_st32(a_lane + (uint32_t)(so_s * Cfg::A_COLS), o);
+                        pend = so_s;
+                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, tap * p.ncc + ccs);
+                        if (++so_s == C2_NO) { so_s = 0; po_s ^= 1u; }
                     }
-                    float o[Cfg::A_COLS];
-                    if (F16) {
-                        // split-fp16 operand: x = hi + 2^-11 * lo with hi = fp16(x), lo = fp16((x - hi) * 2^11): 22 mantissa
-                        // bits like the TF32 pair, but one K = 16 MMA per term instead of two K = 8 ones.  Columns of the
-                        // stage: [hi: k0..15, two per column][lo: k0..15]; |x| saturates at the fp16 range (65504).
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            uint32_t h, l;
-                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
-                            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
-                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l)
-                                : "f"((v[2 * j + 1] - hf.y) * 2048.f), "f"((v[2 * j] - hf.x) * 2048.f));
-                            o[j] = __uint_as_float(h);
-                            o[8 + j] = __uint_as_float(l);
-                        }
-                    } else {
-                        // columns of the stage: [ks0: hi k0..7 | lo k0..7][ks1: hi k8..15 | lo k8..15]
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float h, l;
-                            split_tf32(v[e], h, l);
-                            o[(e >> 3) * 16 + (e & 7)] = h;
-                            o[(e >> 3) * 16 + 8 + (e & 7)] = l;
-                        }
-                    }
-                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(2, it);
-                    // the tensor-memory store of the set's previous stage completes under this stage's ALU work: it is
-                    // waited for and published only now (the MMA side runs >= 4 stages behind, so nothing waits on it)
-                    if (pend >= 0) {
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(OP_FULL(pend));
-                    }
-                    mbar_wait(OP_EMPTY(so), po ^ 1u);
-                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, it);
-                    tc_fence_after();
-                    if (F16) tmem_st16(a_lane + (uint32_t)(so * Cfg::A_COLS), o);
-                    else     tmem_st32(a_lane + (uint32_t)(so * Cfg::A_COLS), o);
-                    pend = so;
-                    if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, it);
-                }
-                __syncwarp();
-                if ((cc & 1) || cc == p.ncc - 1) {              // second half (or an odd tail) passed: raw stage is free
+                    __syncwarp();                                            // every lane has read its raw row
                     if (lane == 0) mbar_arrive(RAW_EMPTY(sr));
-                    if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                 }
-                if (++cc == p.ncc) {
+                if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
+                so += nst;
+                if (so >= C2_NO) { so -= C2_NO; po ^= 1u; }
+                cc += nst;
+                if (cc == p.ncc) {
                     cc = 0; ++tap;
                     if (need_mask) {
                         if (++ts == p.kw) { ts = 0; ++tr; }
                         ok = (unsigned)(hb + tr * p.dil) < (unsigned)p.H && (unsigned)(wb + ts * p.dil) < (unsigned)p.W;
                     }
                 }
-                if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
         if (pend >= 0) {
