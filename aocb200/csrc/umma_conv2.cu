@@ -81,6 +81,19 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// Packed fp32 arithmetic (two IEEE round-to-nearest operations per issue slot; the transform warps are bound by issue
+// slots, not by the FMA pipe): (x0, x1) <- (x0, x1) * (a0, a1) + (b0, b1) and (x0, x1) <- (x0, x1) * c.
+__device__ __forceinline__ void ffma2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 x, a, b;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
+        "fma.rn.f32x2 x, x, a, b;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
+    asm("{\n\t.reg .b64 x, c;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 c, {%2, %2};\n\t"
+        "mul.rn.f32x2 x, x, c;\n\tmov.b64 {%0, %1}, x;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(c));
+}
+
 // What bounds a stage (clock64 trace of the roles, tools/conv_trace.py): ONE thread issuing 6 tcgen05.mma + 2-3
 // tcgen05.commit per stage needs ~45 cycles per instruction, i.e. 400-550 cycles per stage against 384 (TN=128) / 192
 // (TN=64) cycles of tensor work, and the queue behind it is shallow, so the pipe idles during the loop overhead.  The
@@ -276,16 +289,16 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
                                              : "r"(tab_s + (uint32_t)((C2_MAX_AFFINE_C + ccs * C2_KC + j * 4) * 4)));
-                                v[4 * j] = fmaf(v[4 * j], a4.x, b4.x); v[4 * j + 1] = fmaf(v[4 * j + 1], a4.y, b4.y);
-                                v[4 * j + 2] = fmaf(v[4 * j + 2], a4.z, b4.z); v[4 * j + 3] = fmaf(v[4 * j + 3], a4.w, b4.w);
+                                ffma2(v[4 * j], v[4 * j + 1], a4.x, a4.y, b4.x, b4.y);
+                                ffma2(v[4 * j + 2], v[4 * j + 3], a4.z, a4.w, b4.z, b4.w);
                             }
                             if (p.in_relu) {
 #pragma unroll
                                 for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
                             }
-                            if (!ok) {
+                            if (!__all_sync(0xffffffffu, ok)) {              // warp-uniform: interior tiles skip the selects
 #pragma unroll
-                                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                                for (int e = 0; e < 16; ++e) v[e] = ok ? v[e] : 0.f;
                             }
                         }
                         float o[Cfg::A_COLS];
@@ -294,7 +307,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                             // mantissa bits like the TF32 pair, but one K = 16 MMA per term instead of two K = 8 ones.
                             // Columns of the stage: [hi: k0..15, two per column][lo: k0..15]; |x| saturates at the fp16
                             // range (65504).  hi - x comes from the mixed-precision subtract (one FHADD on the packed
-                            // half, exact in fp32) instead of a half -> float conversion and an FADD.
+                            // half, exact in fp32) instead of a half -> float conversion and an FADD; the affine and the
+                            // 2^11 scale are packed f32x2 operations.
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint32_t h, l;
@@ -303,7 +317,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                                 asm("{\n\t.reg .b16 e0, e1;\n\tmov.b32 {e0, e1}, %2;\n\t"
                                     "sub.rn.f32.f16 %0, e0, %3;\n\tsub.rn.f32.f16 %1, e1, %4;\n\t}"
                                     : "=f"(d0), "=f"(d1) : "r"(h), "f"(v[2 * j]), "f"(v[2 * j + 1]));
-                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d1 * -2048.f), "f"(d0 * -2048.f));
+                                fmul2(d0, d1, -2048.f);
+                                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(d1), "f"(d0));
                                 o[j] = __uint_as_float(h);
                                 o[8 + j] = __uint_as_float(l);
                             }
