@@ -7,11 +7,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libaocb200.so")
+# tooling builds (e.g. AOCB200_BUILD_TAG=trace AOCB200_NVCC_FLAGS=-DAOC_CONV_TRACE for tools/conv_trace.py) go to their own
+# object directory and library name; aocb200.lib loads them when AOCB200_LIB_TAG names the same tag
+TAG = os.environ.get("AOCB200_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libaocb200%s.so" % ("_" + TAG if TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("AOCB200_NVCC_FLAGS", "").split()
 
 
 def _newer(a, b):

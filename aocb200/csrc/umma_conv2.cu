@@ -65,12 +65,18 @@ struct Conv2P {
     float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
     unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event][stage < 256]
     int vec_out;
+    int dbg;                // tooling build only (tools/conv_attrib.py): ablation bits, see C2_DBG
 };
 
 #ifdef AOC_CONV_TRACE   // tooling build only (tools/conv_trace.py): keeps the production kernel's code small
 #define C2_TRACE(ev, st) do { if (p.trace && blockIdx.x == 0 && (st) < 256) p.trace[(ev) * 256 + (st)] = clock64(); } while (0)
+// ablation switches of the tooling build (aoc_set_option("conv_dbg", bits); results are garbage, the timing is the point):
+// 1 no weight copies (the barrier is completed by a plain arrive), 2 no activation TMA, 4 no correction MMAs,
+// 8 no transform arithmetic (zeros are stored), 16 no main MMAs
+#define C2_DBG(bit) ((p.dbg & (bit)) != 0)
 #else
 #define C2_TRACE(ev, st) do { } while (0)
+#define C2_DBG(bit) false
 #endif
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -274,12 +280,16 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(1, tap * p.ncc + ccs);
                         float v[16];
                         const uint32_t c8 = (uint32_t)hs * 4u;
+                        if (C2_DBG(8)) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                        } else
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                          : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
                                          : "r"(rawb + (((c8 + j) ^ sw) << 4)));
-                        if (affine) {
+                        if (affine && !C2_DBG(8)) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float4 a4, b4;
@@ -548,9 +558,13 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 for (int rr = tl.r0; rr < tl.r1; ++rr) {
                     mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
                     C2_TRACE(0, 2 * rr);
-                    mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
-                    tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil, hbase + r * p.dil,
-                                tl.n, RAW_FULL(sr));
+                    if (C2_DBG(2)) {
+                        mbar_arrive(RAW_FULL(sr));
+                    } else {
+                        mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
+                        tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil, hbase + r * p.dil,
+                                    tl.n, RAW_FULL(sr));
+                    }
                     if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                     if (++rc == nrc) {
                         rc = 0; ++tap;
@@ -572,6 +586,11 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
                 for (int it = tl.it0; it < tl.it1; ++it) {
                     mbar_wait(OP_EMPTY(sb_), pb ^ 1u);
+                    if (C2_DBG(1)) {
+                        mbar_arrive(B_FULL(sb_));
+                        if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(B_FULL(sb_), Cfg::B_BYTES);
                     const uint32_t sb = op0 + sb_ * Cfg::B_BYTES;
                     const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
@@ -611,7 +630,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
                     const uint32_t d_main = tb + (uint32_t)(b * TN);
                     const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
-                    if (F16) {
+                    if (C2_DBG(16)) {
+                    } else if (F16) {
                         mma_f16_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
                     } else {
                         mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
@@ -647,7 +667,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 if (elect_one()) {
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
                     const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
-                    if (F16) {
+                    if (C2_DBG(4)) {
+                    } else if (F16) {
                         // smem stage = [hi block | lo block] of TN rows x 32 B; TMEM stage = [hi: 8 columns | lo: 8 columns]
                         mma_f16_ts(d_corr, ta + 8, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, it > tl.it0 ? 1u : 0u);
                         mma_f16_ts(d_corr, ta, smem_desc(sb + TN * 32, LBO_BYTES, SBO_BYTES), idesc, 1u);
@@ -850,6 +871,7 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
 }
 
 int g_conv_chunk = 8;   // aoc_set_option("conv_chunk", stages): default accumulation chain length
+int g_conv_dbg = 0;     // aoc_set_option("conv_dbg", bits): ablation switches, honoured by the tooling build only (C2_DBG)
 unsigned long long* g_conv_trace = nullptr;
 
 }  // namespace aoc
@@ -942,6 +964,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.chunk = chunk_stages > 0 ? chunk_stages : g_conv_chunk;
     p.taps = kh * kw;
     p.trace = g_conv_trace;
+    p.dbg = g_conv_dbg;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
     p.tw_log2 = best_l2;

@@ -9,7 +9,8 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(_HERE, "..", "include", "aocb200.h")
-LIB_PATH = os.path.join(_HERE, "libaocb200.so")
+_TAG = os.environ.get("AOCB200_LIB_TAG", "")          # tooling builds only (see build.py); the product library has no tag
+LIB_PATH = os.path.join(_HERE, "libaocb200%s.so" % ("_" + _TAG if _TAG else ""))
 
 _CT = {
     "int": ctypes.c_int, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong,

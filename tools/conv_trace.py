@@ -21,11 +21,13 @@ def main():
         w = (torch.randn(Cout, k, k, Cin, generator=g) / (Cin * k * k) ** 0.5).to(dev)
         eng.w.conv[name] = (w, None, (Cout, k, k, Cin))
         out = eng.conv(x, name, pad=pad)
+        eng.L.set_option(b"conv_dbg", int(os.environ.get("CONV_DBG", "0")))      # ablation bits (tools/conv_attrib.py)
         buf = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
         eng.L.conv_trace(buf.data_ptr())
         eng.conv(x, name, pad=pad, out=out)
         torch.cuda.synchronize()
         eng.L.conv_trace(None)
+        eng.L.set_option(b"conv_dbg", 0)
         tr = buf.cpu().view(8, 256)
         t0 = int(tr[0, 0])
         print(name)
