@@ -63,7 +63,7 @@ struct Conv2P {
     int tiles_n, total_tiles;
     int ksplit;             // split-K factor: work item = (tile, K slice); slices write raw partial sums to `ws`
     float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
-    unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event][stage < 256]
+    unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event < 16][stage < 256]
     int vec_out;
     int dbg;                // tooling build only (tools/conv_attrib.py): ablation bits, see C2_DBG
 };
@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             for (int ch = 0; ch < nchunks; ++ch) {
                 if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
                 else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
+                if (threadIdx.x == 256) C2_TRACE(11, tl.it0 + ch * p.chunk);
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
+                if (threadIdx.x == 256) C2_TRACE(12, tl.it0 + ch * p.chunk);
                 b ^= 1;
             }
             // the correction terms are issued by their own warp: wait for its end-of-tile commit
@@ -586,6 +588,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
                 for (int it = tl.it0; it < tl.it1; ++it) {
                     mbar_wait(OP_EMPTY(sb_), pb ^ 1u);
+                    C2_TRACE(8, it);
                     if (C2_DBG(1)) {
                         mbar_arrive(B_FULL(sb_));
                         if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
@@ -663,6 +666,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             for (int it = tl.it0; it < tl.it1; ++it) {
                 mbar_wait(B_FULL(so), po);
                 mbar_wait(OP_FULL(so), po);
+                if (lane == 0) C2_TRACE(9, it);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t sb = op0 + so * Cfg::B_BYTES;
@@ -691,6 +695,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     if (it == tl.it1 - 1) mma_commit(CORR_FULL(cb));
                 }
                 __syncwarp();
+                if (lane == 0) C2_TRACE(10, it);
                 if (++so == C2_NO) { so = 0; po ^= 1u; }
             }
             if (NCB == 2) cb ^= 1;
@@ -923,8 +928,8 @@ extern "C" size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh
     return (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
 }
 
-extern "C" int aoc_conv_trace(void* device_buffer_8x256_u64) {
-    g_conv_trace = (unsigned long long*)device_buffer_8x256_u64;
+extern "C" int aoc_conv_trace(void* device_buffer_16x256_u64) {
+    g_conv_trace = (unsigned long long*)device_buffer_16x256_u64;
     return AOC_OK;
 }
 

@@ -84,7 +84,7 @@ size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, i
 int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride, int pad, int dil);
 /* tooling: when non-null, CTA 0 of every later aoc_conv2d_nhwc_tc launch records clock64() of its pipeline events
  * (8 events x the first 256 stages, uint64) into this device buffer; see tools/conv_trace.py.  NULL switches it off. */
-int aoc_conv_trace(void* device_buffer_8x256_u64);
+int aoc_conv_trace(void* device_buffer_16x256_u64);
 int aoc_tile_stats_reduce_f32(const float* tile_stats, int N, int tiles_per_image, int C, double* stats,
                               cudaStream_t stream);
 /* depthwise 3x3 pad 1 + bias (aocnet.py:19 seperate_conv); w [C][3][3] */

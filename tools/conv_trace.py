@@ -8,7 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aocb200.engine import Engine, T  # noqa: E402
 from aocb200.params import synthetic_state_dict  # noqa: E402
 
-EV = ["tma_issue(raw)", "raw_seen", "alu_done", "op_empty_seen", "published", "mma:b_full", "mma:op_full", "mma:issued"]
+EV = ["tma_issue(raw)", "raw_seen", "alu_done", "op_empty_seen", "published", "mma:b_full", "mma:op_full", "mma:issued",
+      "w:slot_free", "corr:ready", "corr:issued", "drain:full", "drain:done"]
+NEV = 16
 
 
 def main():
@@ -22,18 +24,18 @@ def main():
         eng.w.conv[name] = (w, None, (Cout, k, k, Cin))
         out = eng.conv(x, name, pad=pad)
         eng.L.set_option(b"conv_dbg", int(os.environ.get("CONV_DBG", "0")))      # ablation bits (tools/conv_attrib.py)
-        buf = torch.zeros(8 * 256, dtype=torch.int64, device=dev)
+        buf = torch.zeros(NEV * 256, dtype=torch.int64, device=dev)
         eng.L.conv_trace(buf.data_ptr())
         eng.conv(x, name, pad=pad, out=out)
         torch.cuda.synchronize()
         eng.L.conv_trace(None)
         eng.L.set_option(b"conv_dbg", 0)
-        tr = buf.cpu().view(8, 256)
+        tr = buf.cpu().view(NEV, 256)
         t0 = int(tr[0, 0])
         print(name)
         print("stage " + " ".join("%15s" % e for e in EV))
-        for s in list(range(0, 24)) + list(range(100, 112)):
-            print("%5d " % s + " ".join("%15d" % (int(tr[e, s]) - t0 if int(tr[e, s]) else -1) for e in range(8)))
+        for s in list(range(0, 12)) + list(range(96, 120)):
+            print("%5d " % s + " ".join("%15d" % (int(tr[e, s]) - t0 if int(tr[e, s]) else -1) for e in range(len(EV))))
         d = (tr[7, 120] - tr[7, 40]).item() / 80.0
         print("steady state: %.0f cycles per stage (MMA issue to MMA issue, stages 40..120)" % d)
 
