@@ -154,9 +154,14 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     const uint32_t bar0 = smem_u32(bars);
     auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
     auto RAW_EMPTY = [&](int s) { return bar0 + 8u * (C2_NR + s); };
-    auto OP_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + s); };                       // activation operand (TMEM)
-    auto OP_EMPTY = [&](int s) { return bar0 + 8u * (2 * C2_NR + C2_NO + s); };              // both operands of a stage
-    auto B_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + s); };            // weight operand (smem)
+    // The operand ring is synchronised per PAIR of stages (slots 2q, 2q+1) and with ONE "full" barrier for both operands:
+    // a try_wait occupies its warp for ~100 cycles even on a completed barrier and try_waits do not overlap (measured:
+    // four back-to-back try_waits on completed barriers = 460 cycles), and the MMA-issuing warps -- the pace setters of
+    // the kernel: ~385 cycles per stage with or without MMAs, copies or arithmetic (tools/conv_attrib.py) -- spent two
+    // of them per stage.  OP_FULL(q) collects the four transform warps' arrivals and the weight copy's
+    // arrive.expect_tx of both stages (count 10); OP_EMPTY(q) the issuers' commits after the pair's second stage.
+    auto OP_FULL = [&](int q) { return bar0 + 8u * (2 * C2_NR + q); };
+    auto OP_EMPTY = [&](int q) { return bar0 + 8u * (2 * C2_NR + C2_NO + q); };
     auto CORR_FULL = [&](int s) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + C2_NB + s); };
     auto MAIN_FULL = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + b); };
     auto MAIN_EMPTY = [&](int b) { return bar0 + 8u * (2 * C2_NR + 2 * C2_NO + 2 * C2_NB + 2 + b); };
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     asm volatile("griddepcontrol.launch_dependents;");
     if (warp == 17 && lane == 0) {
         for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
-        for (int s = 0; s < C2_NO; ++s) { mbar_init(OP_FULL(s), 4); mbar_init(OP_EMPTY(s), 1 + NCI); mbar_init(B_FULL(s), 1); }
+        for (int q = 0; q < C2_NO / 2; ++q) { mbar_init(OP_FULL(q), 10); mbar_init(OP_EMPTY(q), 1 + NCI); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), NCI);
         }
@@ -349,9 +354,10 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                             tmem_st_wait();
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(OP_FULL(pend));
+                            if (lane == 0) mbar_arrive(OP_FULL(pend >> 1));
                         }
-                        mbar_wait(OP_EMPTY(so_s), po_s ^ 1u);
+                        // the slot's pair was released as a whole: one wait per pair the box touches
+                        if (hs == 0 || (so_s & 1) == 0) mbar_wait(OP_EMPTY(so_s >> 1), po_s ^ 1u);
                         if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, tap * p.ncc + ccs);
                         tc_fence_after();
                         if (F16) tmem_st16(a_lane + (uint32_t)(so_s * Cfg::A_COLS), o);
@@ -360,8 +366,13 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, tap * p.ncc + ccs);
                         if (++so_s == C2_NO) { so_s = 0; po_s ^= 1u; }
                     }
-                    __syncwarp();                                            // every lane has read its raw row
-                    if (lane == 0) mbar_arrive(RAW_EMPTY(sr));
+                    // the box's last stage is published before the set moves on (deferred to the set's next box, two
+                    // stage times later, it would hold back the pair the MMA side waits for)
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();                                            // (every lane has also read its raw row)
+                    if (lane == 0) { mbar_arrive(OP_FULL(pend >> 1)); mbar_arrive(RAW_EMPTY(sr)); }
+                    pend = -1;
                 }
                 if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                 so += nst;
@@ -376,12 +387,10 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 }
             }
         }
-        if (pend >= 0) {
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(OP_FULL(pend));
-        }
+        // an odd number of stages leaves the last pair half filled: the issuers wait for whole pairs, so one set (and the
+        // weight producer) supply the missing stage's arrivals
+        // (the set that owned the last box: its real arrival for that pair is already in, so the phase is the right one)
+        if ((so & 1) && ((bi - 1) & 1) == g && lane == 0) mbar_arrive(OP_FULL(so >> 1));
     } else if (warp < 16) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
         // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
@@ -587,26 +596,28 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
                 for (int it = tl.it0; it < tl.it1; ++it) {
-                    mbar_wait(OP_EMPTY(sb_), pb ^ 1u);
+                    if ((sb_ & 1) == 0) mbar_wait(OP_EMPTY(sb_ >> 1), pb ^ 1u);
                     C2_TRACE(8, it);
+                    const uint32_t bfull = OP_FULL(sb_ >> 1);
                     if (C2_DBG(1)) {
-                        mbar_arrive(B_FULL(sb_));
+                        mbar_arrive(bfull);
                         if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
                         continue;
                     }
-                    mbar_arrive_expect_tx(B_FULL(sb_), Cfg::B_BYTES);
+                    mbar_arrive_expect_tx(bfull, Cfg::B_BYTES);
                     const uint32_t sb = op0 + sb_ * Cfg::B_BYTES;
                     const uint8_t* src = wsrc + (size_t)it * C2_WCHUNK;
                     if (TN == C2_WRB) {
-                        bulk_g2s(sb, src, C2_WCHUNK, B_FULL(sb_));
+                        bulk_g2s(sb, src, C2_WCHUNK, bfull);
                     } else {
 #pragma unroll
                         for (int blk = 0; blk < (F16 ? 2 : 4); ++blk)
-                            bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, B_FULL(sb_));
+                            bulk_g2s(sb + blk * (TN * 32), src + blk * 4096 + sub, TN * 32, bfull);
                     }
                     if (++sb_ == C2_NB) { sb_ = 0; pb ^= 1u; }
                 }
             }
+            if (sb_ & 1) mbar_arrive(OP_FULL(sb_ >> 1));          // odd stage count: complete the last pair (see transform)
         }
     } else if (warp == 18) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
@@ -619,9 +630,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             const Tile tl = decode(t);
             int in_chunk = 0;
             for (int it = tl.it0; it < tl.it1; ++it) {
-                mbar_wait(B_FULL(so), po);
                 if (lane == 0) C2_TRACE(5, it);
-                mbar_wait(OP_FULL(so), po);
+                if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);      // both operands of both stages of the pair
                 if (lane == 0) C2_TRACE(6, it);
                 if (in_chunk == 0) {
                     if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
@@ -640,7 +650,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
                         mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
                     }
-                    mma_commit(OP_EMPTY(so));
+                    if (so & 1) mma_commit(OP_EMPTY(so >> 1));
                     if (last) mma_commit(MAIN_FULL(b));
                 }
                 __syncwarp();
@@ -664,8 +674,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
             const Tile tl = decode(t);
             for (int it = tl.it0; it < tl.it1; ++it) {
-                mbar_wait(B_FULL(so), po);
-                mbar_wait(OP_FULL(so), po);
+                if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);
                 if (lane == 0) C2_TRACE(9, it);
                 tc_fence_after();
                 if (elect_one()) {
@@ -691,7 +700,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                             mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, first);
                         }
                     }
-                    mma_commit(OP_EMPTY(so));
+                    if (so & 1) mma_commit(OP_EMPTY(so >> 1));
                     if (it == tl.it1 - 1) mma_commit(CORR_FULL(cb));
                 }
                 __syncwarp();
