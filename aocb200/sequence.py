@@ -85,6 +85,7 @@ class DeviceSequence:
         self.dev = device if device is not None else self.eng.dev
         self.K, self.mem_every = int(num_objects), int(mem_every)
         self.eng.unc_ratio = float(unc_ratio)
+        self.eng.set_seen_labels(None)                                          # reset; the first ground-truth frame sets the list
         self.gt_ids = torch.tensor([self.K], device=self.dev)
         self.ref_e, self.ref_m = [], []
         self.prev_e = self.prev_m = None
