@@ -629,34 +629,56 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             int in_chunk = 0;
-            for (int it = tl.it0; it < tl.it1; ++it) {
+            // Two stages (one operand pair) per iteration where the pair lies inside the tile: one barrier wait, one
+            // tcgen05 fence, one elect and one warp sync for both -- this warp's iteration is the period of the kernel
+            // (DESIGN section 4), every instruction in front of its tcgen05.mma counts.
+            for (int it = tl.it0; it < tl.it1;) {
+                const int n = ((so & 1) == 0 && it + 1 < tl.it1) ? 2 : 1;
                 if (lane == 0) C2_TRACE(5, it);
                 if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);      // both operands of both stages of the pair
                 if (lane == 0) C2_TRACE(6, it);
-                if (in_chunk == 0) {
-                    if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
-                    else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
+                // accumulator bookkeeping of the stages: a chain of `chunk` stages per MAIN buffer, a chain's first stage
+                // waits for the drain warps to have read the buffer's previous chain
+                int bb[2], ic[2];
+                bool ls[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k < n) {
+                        bb[k] = b; ic[k] = in_chunk;
+                        if (in_chunk == 0) {
+                            if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
+                            else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
+                        }
+                        ls[k] = (in_chunk + 1 == p.chunk) || (it + k == tl.it1 - 1);
+                        if (ls[k]) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
+                    }
                 }
                 tc_fence_after();
-                const bool last = (in_chunk + 1 == p.chunk) || (it == tl.it1 - 1);
                 if (elect_one()) {
-                    const uint32_t sb = op0 + so * Cfg::B_BYTES;
-                    const uint32_t d_main = tb + (uint32_t)(b * TN);
-                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
-                    if (C2_DBG(16)) {
-                    } else if (F16) {
-                        mma_f16_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
-                    } else {
-                        mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, in_chunk > 0 ? 1u : 0u);
-                        mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (k < n) {
+                            const int slot = so + k;                     // n == 2 only on an even slot: no wrap inside
+                            const uint32_t sb = op0 + slot * Cfg::B_BYTES;
+                            const uint32_t d_main = tb + (uint32_t)(bb[k] * TN);
+                            const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(slot * Cfg::A_COLS);
+                            if (C2_DBG(16)) {
+                            } else if (F16) {
+                                mma_f16_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, ic[k] > 0 ? 1u : 0u);
+                            } else {
+                                mma_tf32_ts(d_main, ta, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, ic[k] > 0 ? 1u : 0u);
+                                mma_tf32_ts(d_main, ta + 16, smem_desc(sb + TN * 64, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                            }
+                            if (slot & 1) mma_commit(OP_EMPTY(slot >> 1));
+                            if (ls[k]) mma_commit(MAIN_FULL(bb[k]));
+                        }
                     }
-                    if (so & 1) mma_commit(OP_EMPTY(so >> 1));
-                    if (last) mma_commit(MAIN_FULL(b));
                 }
                 __syncwarp();
                 if (lane == 0) C2_TRACE(7, it);
-                if (last) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
-                if (++so == C2_NO) { so = 0; po ^= 1u; }
+                it += n;
+                so += n;
+                if (so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
     } else if (warp >= 19 && warp < 19 + NCI) {
@@ -673,39 +695,48 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
             else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
             const Tile tl = decode(t);
-            for (int it = tl.it0; it < tl.it1; ++it) {
+            for (int it = tl.it0; it < tl.it1;) {                      // two stages per iteration, as in the MAIN issuer
+                const int n = ((so & 1) == 0 && it + 1 < tl.it1) ? 2 : 1;
                 if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);
                 if (lane == 0) C2_TRACE(9, it);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t sb = op0 + so * Cfg::B_BYTES;
-                    const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(so * Cfg::A_COLS);
-                    if (C2_DBG(4)) {
-                    } else if (F16) {
-                        // smem stage = [hi block | lo block] of TN rows x 32 B; TMEM stage = [hi: 8 columns | lo: 8 columns]
-                        mma_f16_ts(d_corr, ta + 8, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, it > tl.it0 ? 1u : 0u);
-                        mma_f16_ts(d_corr, ta, smem_desc(sb + TN * 32, LBO_BYTES, SBO_BYTES), idesc, 1u);
-                    } else
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
-                        const uint32_t ta_hi = ta + (uint32_t)(ks * 16), ta_lo = ta_hi + 8;
-                        const uint32_t first = (it > tl.it0 || ks > 0) ? 1u : 0u;
-                        if (NCI == 1) {
-                            mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
-                            mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
-                        } else if (ci == 0) {
-                            mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
-                        } else {
-                            mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, first);
+                    for (int k = 0; k < 2; ++k) {
+                        if (k < n) {
+                            const int slot = so + k, itk = it + k;
+                            const uint32_t sb = op0 + slot * Cfg::B_BYTES;
+                            const uint32_t ta = tb + Cfg::A_TMEM_COL + (uint32_t)(slot * Cfg::A_COLS);
+                            if (C2_DBG(4)) {
+                            } else if (F16) {
+                                // smem stage = [hi block | lo block] of TN rows x 32 B; TMEM stage = [hi: 8 columns | lo: 8 columns]
+                                mma_f16_ts(d_corr, ta + 8, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, itk > tl.it0 ? 1u : 0u);
+                                mma_f16_ts(d_corr, ta, smem_desc(sb + TN * 32, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                            } else
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint32_t b_hi = sb + ks * (TN * 64), b_lo = b_hi + TN * 32;
+                                const uint32_t ta_hi = ta + (uint32_t)(ks * 16), ta_lo = ta_hi + 8;
+                                const uint32_t first = (itk > tl.it0 || ks > 0) ? 1u : 0u;
+                                if (NCI == 1) {
+                                    mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
+                                    mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                                } else if (ci == 0) {
+                                    mma_tf32_ts(d_corr, ta_lo, smem_desc(b_hi, LBO_BYTES, SBO_BYTES), idesc, first);
+                                } else {
+                                    mma_tf32_ts(d_corr, ta_hi, smem_desc(b_lo, LBO_BYTES, SBO_BYTES), idesc, first);
+                                }
+                            }
+                            if (slot & 1) mma_commit(OP_EMPTY(slot >> 1));
+                            if (itk == tl.it1 - 1) mma_commit(CORR_FULL(cb));
                         }
                     }
-                    if (so & 1) mma_commit(OP_EMPTY(so >> 1));
-                    if (it == tl.it1 - 1) mma_commit(CORR_FULL(cb));
                 }
                 __syncwarp();
                 if (lane == 0) C2_TRACE(10, it);
-                if (++so == C2_NO) { so = 0; po ^= 1u; }
+                it += n;
+                so += n;
+                if (so == C2_NO) { so = 0; po ^= 1u; }
             }
             if (NCB == 2) cb ^= 1;
         }
