@@ -70,6 +70,18 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        # the sampler must be gone before anything else is timed: a monitoring process that is still tearing down its
+        # driver handle can hold up launches / synchronisations of the run that follows (seen once as a 70 ms stall
+        # inside the end-to-end region)
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        self.t.join(timeout=2)
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
