@@ -9,13 +9,16 @@
 // stages of 16 input channels of one filter tap; 20 warps, register file re-partitioned per role with setmaxnreg):
 //   warp 16    TMA: cp.async.bulk.tensor.4d of the raw fp32 input patch [th][tw][32 channels] (zero fill = conv padding,
 //              element strides = conv stride, 128B swizzle) into a 6-deep ring; one box feeds two operand stages
-//   warps 0-7  transform, two sets of four owning alternate stages (thread = pixel = TMEM lane): raw -> (optional a*x+b,
-//              ReLU, padding mask) -> operand split -> tcgen05.st into an operand ring in TENSOR memory.  Operand formats:
+//   warps 0-7  transform, two sets of four owning alternate raw boxes = pairs of stages (thread = pixel = TMEM lane): raw ->
+//              (optional a*x+b, ReLU, padding mask) -> operand split -> tcgen05.st into an operand ring in TENSOR memory.
+//              Operand formats:
 //              split-fp16 (default): hi = fp16(x), lo = fp16((x - hi) * 2^11), one K = 16 kind::f16 MMA per term;
 //              3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi), two K = 8 kind::tf32 MMAs per term
 //   warp 17    TMA bulk copies of the pre-split weight image into the shared-memory operand ring
 //   warps 18/19  warp-uniform loops, one elected lane issues tcgen05.mma with the A operand from TMEM:
-//              hi*hi -> MAIN accumulator (warp 18), lo*hi + hi*lo -> CORR accumulator (warp 19)
+//              hi*hi -> MAIN accumulator (warp 18), lo*hi + hi*lo -> CORR accumulator (warp 19); the operand ring is
+//              synchronised per pair of stages (one full barrier for both operands, one empty barrier) and an issuer
+//              iteration covers a pair
 //   warps 8-15 drain: every `chunk` stages the MAIN accumulator (double buffered in TMEM) is read with tcgen05.ld and
 //              added to fp32 registers with round-to-nearest; the epilogue adds CORR (x 2^-11 for split-fp16), transposes
 //              through shared memory, applies bias, residual, ReLU, writes 128-byte lines and per-tile statistics.
@@ -100,11 +103,14 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
         : "+f"(x0), "+f"(x1) : "f"(c));
 }
 
-// What bounds a stage (clock64 trace of the roles, tools/conv_trace.py): ONE thread issuing 6 tcgen05.mma + 2-3
-// tcgen05.commit per stage needs ~45 cycles per instruction, i.e. 400-550 cycles per stage against 384 (TN=128) / 192
-// (TN=64) cycles of tensor work, and the queue behind it is shallow, so the pipe idles during the loop overhead.  The
-// issue work is therefore split over TWO warps -- one feeds the MAIN accumulator (2 MMAs per stage), one the CORR
-// accumulator (4 MMAs per stage) -- and a stage's operands are released by one shared barrier (2 commits).
+// What bounds a stage (clock64 trace of the roles, tools/conv_trace.py; ablation runs, tools/conv_attrib.py): the
+// iteration of the MMA-issuing warps, not the tensor pipe, the copies or the transform arithmetic (83 % of the time is
+// left with all of those switched off).  First finding (3xTF32 days): ONE thread issuing 6 tcgen05.mma + 2-3
+// tcgen05.commit per stage needed 400-550 cycles per stage, so the issue work is split over TWO warps -- one feeds the
+// MAIN accumulator, one the CORR accumulator.  Second finding (split-fp16, 3 MMAs per stage = 192-222 tensor cycles):
+// the MAIN issuer's iteration -- barrier waits (~100 cycles per try_wait, not overlappable), tcgen05 fence, elect, the
+// uniform-register chain in front of each tcgen05 instruction, on a sub-partition shared with four busy warps -- took
+// ~385 cycles per stage, hence one full barrier per PAIR of stages for both operands and two stages per iteration.
 template <int TN, bool F16>
 struct C2Cfg {
     static constexpr int NR = 6;                             // raw activation ring depth (128 pixels x 32 channels each)
