@@ -44,3 +44,45 @@ def test_eval_loop_bookkeeping():
     assert stub.calls[4]["prev_m"][0, 0, 3, 3] == 2
     # frame 4: id 2 has been seen now -> it wins wherever the stub says so
     assert (preds[3][1:, :] == 2).all() and preds[3][0, 0] == 0
+
+
+class _Replay:
+    """the recording stub of tools/make_eval_loop_golden.py: frame t's probabilities are fixed, every call is recorded"""
+
+    def __init__(self, probs):
+        self.probs, self.calls, self.t = probs, [], 0
+
+    def forward_for_eval(self, memory, ref_e, ref_m, prev_e, prev_m, img, pred_size=None, gt_ids=None):
+        self.calls.append(dict(n_ref=len(ref_e), ref_m=[m.clone().long().view(m.shape[-2], m.shape[-1]) for m in ref_m],
+                               prev_m=None if prev_m is None else prev_m.clone().long().view(prev_m.shape[-2], prev_m.shape[-1])))
+        t = self.t
+        self.t += 1
+        emb = torch.full((1, 4, 2, 2), float(t))
+        return (None if prev_e is None else self.probs[t:t + 1].clone()), emb, memory
+
+
+def test_run_sequence_matches_the_reference_eval_loop():
+    """tests/golden/eval_loop_trace.pt holds what the REFERENCE's own `Evaluator.evaluating()`
+    (networks/engine/eval_manager_mm.py:160-394, run unmodified by tools/make_eval_loop_golden.py) handed to the model
+    on every call and the label maps it saved, for four synthetic sequences (absent id, id joining with ground truth,
+    join on a memory frame, no candidate pool).  run_sequence must reproduce all of it bit for bit."""
+    import os
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "eval_loop_trace.pt"))
+    assert len(cases) == 4
+    for c in cases:
+        stub = _Replay(c["probs"])
+        later = {t: lab for t, lab in c["labels"].items() if t != 0}
+        preds = run_sequence(stub, torch.zeros(c["T"], 3, c["H"], c["W"]), c["labels"][0], c["K"],
+                             mem_every=c["mem_every"], unc_ratio=c["unc_ratio"], later_labels=later)
+        assert len(preds) == len(c["saved"]) == c["T"] - 1
+        for t, (a, b) in enumerate(zip(preds, c["saved"])):
+            assert torch.equal(a.long(), b), ("saved label map", c["seed"], t + 1)
+        assert len(stub.calls) == len(c["calls"])
+        for t, (a, b) in enumerate(zip(stub.calls, c["calls"])):
+            assert a["n_ref"] == b["n_ref"], ("bank length", c["seed"], t)
+            assert (a["prev_m"] is None) == (b["prev_m"] is None)
+            if a["prev_m"] is not None:
+                assert torch.equal(a["prev_m"], b["prev_m"]), ("previous mask", c["seed"], t)
+            assert len(a["ref_m"]) == len(b["ref_m"])
+            for i, (x, y) in enumerate(zip(a["ref_m"], b["ref_m"])):
+                assert torch.equal(x, y), ("bank label map", c["seed"], t, i)
