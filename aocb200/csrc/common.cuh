@@ -23,6 +23,34 @@ inline int launch_status(const char* what) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (opt-in dynamic shared memory) and the SM count belong to a DEVICE, not to the process: a host
+// that drives engines on several GPUs from one process must set / query them once per device ordinal.
+constexpr int AOC_MAX_DEVICES = 64;
+struct PerDeviceOnce {
+    bool done[AOC_MAX_DEVICES] = {};
+    // true exactly once per current device (and always for ordinals beyond the table: the attribute call is cheap)
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= AOC_MAX_DEVICES) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+inline int device_sms() {
+    static int sms[AOC_MAX_DEVICES] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool tab = dev >= 0 && dev < AOC_MAX_DEVICES;
+    if (tab && sms[dev] > 0) return sms[dev];
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (tab) sms[dev] = n;
+    return n;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

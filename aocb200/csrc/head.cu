@@ -81,8 +81,9 @@ __global__ void upsample_softmax_kernel(const float* __restrict__ logits, float*
 
 // The eval loop's per-frame label bookkeeping fused behind the upsample + softmax (eval_manager_mm.py:252-270 label
 // filter, :318-320 argmax, :339-349 uncertainty filter; shannon_entropy.py:10-13):
-//   probs[o] = softmax_o(upsampled logits) for labels seen in a ground-truth frame so far, 0 otherwise
-//   label    = argmax_o probs (lowest index wins ties, as torch.argmax)
+//   probs[o] = softmax_o(upsampled logits), unfiltered: what AOCNet.forward_for_eval returns (optional output)
+//   p_o      = probs[o] for labels seen in a ground-truth frame so far, 0 otherwise
+//   label    = argmax_o p_o (lowest index wins ties, as torch.argmax)
 //   ent      = -sum_{o seen} p_o * log(p_o + 1e-6)
 //   conf     = ent > unc_ratio ? 125 : label      (125 = "uncertain": matches no object slot in the memory bank)
 // exist: device word, bit o set <=> label o has been seen (null = all); a device word so that a captured graph follows
@@ -116,8 +117,9 @@ __global__ void upsample_softmax_label_kernel(const float* __restrict__ logits, 
     int am = 0;
     for (int o = 0; o < O; ++o) {
         const bool seen = (ex >> o) & 1u;
-        const float pr = seen ? v[o] * inv : 0.f;
-        probs[(size_t)o * H * W + i] = pr;
+        const float pa = v[o] * inv;
+        if (probs) probs[(size_t)o * H * W + i] = pa;
+        const float pr = seen ? pa : 0.f;
         if (pr > best) { best = pr; am = o; }
         if (seen) ent += pr * logf(pr + 1e-6f);
     }
@@ -157,7 +159,7 @@ extern "C" int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8
 extern "C" int aoc_upsample_softmax_label_f32(const float* logits, float* probs, uint8_t* label, uint8_t* conf_label,
                                               float* entropy, const int* exist_bits, float unc_ratio, int O, int h,
                                               int w, int H, int W, cudaStream_t stream) {
-    AOC_CHECK_ARG(logits && probs && label, "null pointer");
+    AOC_CHECK_ARG(logits && label, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= AOC_MAX_OBJECTS && h > 0 && w > 0 && H > 0 && W > 0, "bad dims");
     float sh = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f;
     float sw = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;

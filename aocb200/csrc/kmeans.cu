@@ -282,11 +282,10 @@ extern "C" int aoc_kmeans_proxies_f32(const float* S, const int* meta, const int
     int nb = cdiv(m, rpb);
     float* part = (float*)workspace;
     int* pcnt = (int*)(part + (size_t)O * nb * KM_K * EMB);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(kmeans_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM);
         cudaFuncSetAttribute(kmeans_step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM);
-        attr = true;
     }
     kmeans_init_kernel<<<O, 256, 0, stream>>>(S, meta, kk, init_idx, cent);
     dim3 gs(nb, O), gr(KM_K, O);

@@ -598,11 +598,10 @@ extern "C" int aoc_global_match_simt_f32(const float* q, int HW, const float* S,
                                          const float* bias, int O, float* mins_ws, float* out, cudaStream_t stream) {
     AOC_CHECK_ARG(q && S && r2 && meta && bias && mins_ws && out, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO && HW > 0, "bad dims");
-    static bool attr_done = false;
+    static PerDeviceOnce attr_done;
     size_t smem = (size_t)2 * EMB * GM_LD * sizeof(float);
-    if (!attr_done) {
+    if (attr_done.first()) {
         cudaFuncSetAttribute(global_match_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
     }
     dim3 grid(cdiv(HW, 128), O);
     global_match_simt_kernel<<<grid, 256, smem, stream>>>(q, HW, S, r2, meta, O, mins_ws);
@@ -621,11 +620,10 @@ extern "C" int aoc_proxy_match_f32(const float* q, int HW, const float* P, const
                                    int O, float* out_cluster, float* out_proxy, cudaStream_t stream) {
     AOC_CHECK_ARG(q && P && pvalid && bias && out_cluster && out_proxy, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO && HW > 0, "bad dims");
-    static bool attr_done = false;
+    static PerDeviceOnce attr_done;
     size_t smem = (size_t)(EMB * 128 + EMB * NPX) * sizeof(float);
-    if (!attr_done) {
+    if (attr_done.first()) {
         cudaFuncSetAttribute(proxy_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
     }
     proxy_match_kernel<<<cdiv(HW, 128), 128, smem, stream>>>(q, HW, P, pvalid, bias, O, out_cluster, out_proxy);
     return launch_status("aoc_proxy_match_f32");
@@ -646,11 +644,10 @@ extern "C" int aoc_head_pool_f32(const float* emb, const uint8_t* ids, int total
     float* part = (float*)workspace;
     int* pcnt = (int*)(part + (size_t)nblk * (MAXO + 1) * EMB);
     size_t smem = (size_t)8 * (O + 1) * EMB * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.first()) {
         cudaFuncSetAttribute(head_pool_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((size_t)8 * (MAXO + 1) * EMB * sizeof(float)));
-        attr_done = true;
     }
     head_pool_partial_kernel<<<nblk, 256, smem, stream>>>(emb, ids, total_pixels, O, part, pcnt);
     head_pool_final_kernel<<<O, 128, 0, stream>>>(part, pcnt, nblk, total_pixels, O, eps, head, ld_head, off_pos,

@@ -154,6 +154,30 @@ __global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ x, uint8_t*
     y[i] = x[(size_t)yi * Wi + xi];
 }
 
+// the same for an int64 label map (what torch.argmax hands the reference loop), values clamped to 0..255
+__global__ void resize_nearest_i64_kernel(const long long* __restrict__ x, uint8_t* __restrict__ y, int Hi, int Wi,
+                                          int Ho, int Wo, float sh, float sw) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ho * Wo) return;
+    int yo = i / Wo, xo = i - yo * Wo;
+    int yi = (Ho == Hi) ? yo : min((int)floorf((float)yo * sh), Hi - 1);
+    int xi = (Wo == Wi) ? xo : min((int)floorf((float)xo * sw), Wi - 1);
+    const long long v = x[(size_t)yi * Wi + xi];
+    y[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// out = a (op) b over n floats; op 0: a + b, 1: a * b   (per-(sample, channel) coefficient vectors: a few thousand values)
+__global__ void vec_op_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n,
+                              int op) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = op == 0 ? a[i] + b[i] : a[i] * b[i];
+}
+
 static inline float ac_scale(int in, int out) { return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f; }
 
 }  // namespace aoc
@@ -212,6 +236,29 @@ extern "C" int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int W
                                                                              (float)Hi / (float)Ho,
                                                                              (float)Wi / (float)Wo);
     return launch_status("aoc_resize_nearest_u8");
+}
+
+extern "C" int aoc_resize_nearest_i64(const long long* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo,
+                                      cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad args");
+    resize_nearest_i64_kernel<<<cdiv((long long)Ho * Wo, 256), 256, 0, stream>>>(x, y, Hi, Wi, Ho, Wo,
+                                                                              (float)Hi / (float)Ho,
+                                                                              (float)Wi / (float)Wo);
+    return launch_status("aoc_resize_nearest_i64");
+}
+
+extern "C" int aoc_fill_u32(void* p, unsigned int value, long long n_words, cudaStream_t stream) {
+    AOC_CHECK_ARG(p && n_words > 0 && (((uintptr_t)p) & 3) == 0, "bad args");
+    int blocks = (int)((n_words + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    fill_u32_kernel<<<blocks, 256, 0, stream>>>((uint32_t*)p, value, n_words);
+    return launch_status("aoc_fill_u32");
+}
+
+extern "C" int aoc_vec_op_f32(const float* a, const float* b, float* out, int n, int op, cudaStream_t stream) {
+    AOC_CHECK_ARG(a && b && out && n > 0 && (op == 0 || op == 1), "bad args");
+    vec_op_kernel<<<cdiv(n, 256), 256, 0, stream>>>(a, b, out, n, op);
+    return launch_status("aoc_vec_op_f32");
 }
 
 namespace aoc {

@@ -68,6 +68,7 @@ struct Conv2P {
     float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
     unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event < 16][stage < 256]
     int vec_out;
+    int* overflow;          // optional device word: set to 1 when a split-fp16 activation operand reaches the fp16 range (|x| >= 6e4)
     int dbg;                // tooling build only (tools/conv_attrib.py): ablation bits, see C2_DBG
 };
 
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         int tab_n = -1;
         int bi = 0;                                                          // running raw-box index (parity = owner set)
         int pend = -1;                                                       // operand slot stored but not yet published
+        float amax = 0.f;                                                    // largest |operand| this thread converted to fp16
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
@@ -334,6 +336,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                             for (int j = 0; j < 8; ++j) {
                                 uint32_t h, l;
                                 float d0, d1;
+                                // range guard: one three-input FMNMX per two operands; checked once at the end of the kernel
+                                asm("max.abs.f32 %0, %0, %1, %2;" : "+f"(amax) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
                                 asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
                                 asm("{\n\t.reg .b16 e0, e1;\n\tmov.b32 {e0, e1}, %2;\n\t"
                                     "sub.rn.f32.f16 %0, e0, %3;\n\tsub.rn.f32.f16 %1, e1, %4;\n\t}"
@@ -397,6 +401,9 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         // weight producer) supply the missing stage's arrivals
         // (the set that owned the last box: its real arrival for that pair is already in, so the phase is the right one)
         if ((so & 1) && ((bi - 1) & 1) == g && lane == 0) mbar_arrive(OP_FULL(so >> 1));
+        // cvt.rn.satfinite clamps at 65504: a clamped operand means a wrong result, so it is reported (sticky word; the
+        // host re-runs the frame with 3xTF32 operands, which have the fp32 exponent range)
+        if (F16 && p.overflow && amax >= 6.0e4f) *p.overflow = 1;
     } else if (warp < 16) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
         // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
@@ -861,30 +868,21 @@ static EncodeTiledFn get_encode() {
 
 constexpr int C2_MAX_KSPLIT = 8;
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
-int g_conv_f16 = 1;      // aoc_set_option("conv_f16", 0/1): split-fp16 operands (2 terms, K = 16 MMAs) instead of 3xTF32.
-                         // Read by the weight packer AND the convolution: switch it before any weight is packed.
 int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels
 int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
 
 template <int TN, bool F16>
 static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void* workspace, size_t ws_bytes,
                         cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         cudaFuncSetAttribute(conv2_kernel<TN, false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
         cudaFuncSetAttribute(conv2_kernel<TN, true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
-        attr = true;
     }
     Conv2P q = p;
     q.tiles_n = cdiv(p.Cout, TN);
     q.total_tiles = tiles * q.tiles_n;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    const int sms = device_sms();
     // split-K: a layer with fewer tiles than half the SMs (the 31x54 maps of the backbone: 14 pixel tiles) would leave
     // the chip idle and run its whole K loop -- up to 1152 stages -- on a few SMs; slices of >= 4 raw stages (8 operand
     // stages) spread it.  Needs the caller's workspace for the partial sums; the epilogue fusions (statistics) do not apply.
@@ -929,14 +927,16 @@ unsigned long long* g_conv_trace = nullptr;
 
 using namespace aoc;
 
-extern "C" size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw) {
+extern "C" size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw, int operand_mode) {
     const size_t ncc = (size_t)cdiv(Cin, C2_KC);
-    return (size_t)cdiv(Cout, C2_WRB) * kh * kw * ncc * c2_wchunk(g_conv_f16 != 0);
+    return (size_t)cdiv(Cout, C2_WRB) * kh * kw * ncc * c2_wchunk(operand_mode == AOC_CONV_SPLIT_F16);
 }
 
-extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
-                                            cudaStream_t stream) {
+extern "C" int aoc_conv_pack_weights(const float* w, int Cout, int Cin, int kh, int kw, int operand_mode, void* w_packed,
+                                     cudaStream_t stream) {
     AOC_CHECK_ARG(w && w_packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, "bad args");
+    AOC_CHECK_ARG(operand_mode == AOC_CONV_SPLIT_F16 || operand_mode == AOC_CONV_TF32X3, "unknown operand mode");
+    const int g_conv_f16 = operand_mode == AOC_CONV_SPLIT_F16;
     const int ncc = cdiv(Cin, C2_KC);
     const int rows_padded = cdiv(Cout, C2_WRB) * C2_WRB;
     const long long total = (long long)rows_padded * kh * kw * ncc * (g_conv_f16 ? 2 : 4);
@@ -946,7 +946,7 @@ extern "C" int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, i
         conv2_pack_weights_f16_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
     else
         conv2_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
-    return launch_status("aoc_conv_pack_weights_tf32x3");
+    return launch_status("aoc_conv_pack_weights");
 }
 
 // pixel-patch geometry shared by the launcher and the tile-statistics consumers
@@ -989,9 +989,11 @@ extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride
 extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
                                   const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N,
                                   int H, int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw,
-                                  int stride, int pad, int dil, int relu, int chunk_stages, void* workspace,
-                                  size_t ws_bytes, cudaStream_t stream) {
+                                  int stride, int pad, int dil, int relu, int chunk_stages, int operand_mode,
+                                  int* overflow_flag, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     AOC_CHECK_ARG(x && w_packed && y, "null pointer");
+    AOC_CHECK_ARG(operand_mode == AOC_CONV_SPLIT_F16 || operand_mode == AOC_CONV_TF32X3, "unknown operand mode");
+    const int g_conv_f16 = operand_mode == AOC_CONV_SPLIT_F16;
     AOC_CHECK_ARG(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && dil > 0, "bad dims");
     AOC_CHECK_ARG(stride == 1 || stride == 2, "stride must be 1 or 2");
     AOC_CHECK_ARG(ldx % 4 == 0 && (((uintptr_t)x) & 15) == 0, "ldx must be a multiple of 4 and x 16-byte aligned");
@@ -1016,6 +1018,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.taps = kh * kw;
     p.trace = g_conv_trace;
     p.dbg = g_conv_dbg;
+    p.overflow = overflow_flag;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
     p.tw_log2 = best_l2;

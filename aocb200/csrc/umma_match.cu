@@ -336,7 +336,7 @@ static int pick_splits(int nqt, int nrb) {
     return s;
 }
 
-static bool g_attr0 = false, g_attr1 = false;
+static PerDeviceOnce g_attr0, g_attr1;
 
 }  // namespace aoc
 
@@ -429,10 +429,9 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
     long long n = (long long)HW * O;
     fill_f32_kernel<<<cdiv(n * nsplit, 1024), 256, 0, stream>>>(mins, INFINITY, n * nsplit);
     if (nrb > 0) {
-        if (!g_attr0) {
+        if (g_attr0.first()) {
             cudaFuncSetAttribute(match_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<false>::SMEM);
             cudaFuncSetAttribute(match_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<true>::SMEM);
-            g_attr0 = true;
         }
         dim3 grid(nqt, nsplit);
         if (f16)
@@ -462,9 +461,8 @@ extern "C" int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, in
     if (rc) return rc;
     rc = aoc_pack_tc_image_f32(B, N, K, K, RBK, TC_K, Bi, stream);
     if (rc) return rc;
-    if (!g_attr1) {
+    if (g_attr1.first()) {
         cudaFuncSetAttribute(match_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MATCH);
-        g_attr1 = true;
     }
     dim3 grid(M / QB, 1);
     uint32_t lbo = variant == 1 ? SBO_BYTES : LBO_BYTES, sbo = variant == 1 ? LBO_BYTES : SBO_BYTES;

@@ -58,10 +58,12 @@ class TileStats:
 
 
 class Weights:
-    """Device-resident, repacked parameters (done once per state_dict)."""
+    """Device-resident, repacked parameters (done once per state_dict).  The folding arithmetic (FrozenBatchNorm into the
+    convolutions, the constant branches of the conditioning blocks) runs on the HOST in fp32 and each result is uploaded
+    once: no torch kernel is launched on the device, the first kernels of a fresh engine are the library's own."""
 
     def __init__(self, sd, device):
-        f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+        f = lambda k: sd[k].detach().to(device="cpu", dtype=torch.float32)
         self.dev = device
         self.conv = {}      # name -> (w [Cout,kh,kw,Cin], bias|None, (Cout,kh,kw,Cin))
         self.vec = {}       # misc vectors / matrices
@@ -125,18 +127,25 @@ class Weights:
             c23 = torch.cat([f(p + ".CL_2.mlp_layer.bias"), f(p + ".CL_3.mlp_layer.bias")])
             self.vec[p + ".fold.weight"] = Wm[:, :C].contiguous()
             self.vec[p + ".fold.bias"] = (bm + Wm[:, C:] @ c23).contiguous()
+        # largest |weight| a convolution will see (range check of the split-fp16 operand mode), taken on the host
+        self.conv_wmax = max(float(w.abs().max()) for w, _, _ in self.conv.values())
+        up = lambda t: None if t is None else t.contiguous().to(device)
+        self.conv = {k: (up(w), up(b), shp) for k, (w, b, shp) in self.conv.items()}
+        self.vec = {k: up(v) for k, v in self.vec.items()}
 
 
 class Bank:
     def __init__(self):
-        self.reset()
+        self.version = 0          # bumped whenever frames are appended or the bank is reset; NEVER reused: captured
+        self.reset()              # graphs of the bank-dependent segment are keyed on it (a new sequence's one-frame
+                                  # bank must not match the previous sequence's one-frame bank)
 
     def reset(self):
         self.refs, self.masks = [], []
         self.emb_all = self.ids_all = None
         self.hw = None
         self.n = 0
-        self.version = 0          # bumped whenever frames are appended / the bank is rebuilt
+        self.version += 1
         self.index = None         # object-sorted index of the current version (see Engine._bank_index)
 
 
@@ -163,6 +172,7 @@ class Engine:
         self.cluster_num = 16
         self.debug = {}
         self.keep_debug = False
+        self.force_proxies = None       # test hook, see _apply_forced_proxies
         # tensor-core (tcgen05, 3xTF32) kernels vs the fp32 SIMT kernels; both are CUDA, same results to ~1e-6 relative
         tc = os.environ.get("AOCB200_TC", "1") != "0"
         self.tc_conv = tc and os.environ.get("AOCB200_TC_CONV", "1") != "0"
@@ -171,23 +181,33 @@ class Engine:
         for kv in filter(None, os.environ.get("AOCB200_OPTS", "").split(",")):     # e.g. "conv_pdl=0,conv_splitk=0"
             k, v = kv.split("=")
             self.L.set_option(k.strip().encode(), int(v))
-        # the split-fp16 convolution operands saturate at the fp16 range: weights (FrozenBatchNorm folded in) that do
-        # not fit select the 3xTF32 operand mode for this process (same kernels and tests, ~12 % slower)
-        wmax = max(float(w.abs().max()) for w, _, _ in self.w.conv.values())
-        if not (wmax < 6.0e4):
-            self.L.set_option(b"conv_f16", 0)
+        # Convolution operand mode of THIS engine (a per-call argument of the library, recorded with every packed weight
+        # image).  Split-fp16 operands saturate at the fp16 range: weights (FrozenBatchNorm folded in) that do not fit
+        # select 3xTF32 from the start (same kernels and tests, ~12 % slower); activations are watched by the kernels
+        # themselves (sticky device word `_ovf`, see _overflow_check).
+        self.conv_mode = 1 if self.w.conv_wmax < 6.0e4 else 0       # AOC_CONV_SPLIT_F16 / AOC_CONV_TF32X3
+        if os.environ.get("AOCB200_CONV_MODE", "") in ("tf32", "0"):
+            self.conv_mode = 0
+        self._ovf = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._ovf_ring = [(torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event(), [None]) for _ in range(4)]
+        self._ovf_turn = 0
+        self.overflow_policy = os.environ.get("AOCB200_OVERFLOW", "deferred")    # deferred | sync | off
+        self.overflow_frames = []       # frame counters whose fp16 operands overflowed (results invalid / re-run)
+        self.frame_no = 0
         self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self.use_graphs = os.environ.get("AOCB200_GRAPHS", "1") != "0"
         self._segA, self._static = {}, {}
         self._cap_stream = self._pool = None
-        self._gt_cache = (None, 0)
+        self._gt_cache = (None, 0, 0)
         self._ws_keep = []
         self._ws = {}
         # eval-loop label bookkeeping on the device: bit o of the word = label o was seen in a
         # ground-truth frame (eval_manager_mm.py:252-270); entropy threshold of the confident mask (:339-349)
         self._exist = torch.full((1,), -1, dtype=torch.int32, device=self.dev)
+        self._exist_bits = -1
         self.unc_ratio = 1.0
+        self.want_probs = True          # DeviceSequence switches the [1,O,H,W] probability output off (nobody reads it)
         self.last_logits = self.last_label = self.last_conf_label = None
 
     # ------------------------------------------------------------------ plumbing
@@ -197,6 +217,18 @@ class Engine:
 
     def empty(self, n, dtype=torch.float32):
         return torch.empty(int(n), dtype=dtype, device=self.dev)
+
+    def zeros(self, n, dtype=torch.float32):
+        """zero-filled 32-bit buffer (library fill kernel: no torch kernel inside the captured frame)"""
+        t = torch.empty(int(n), dtype=dtype, device=self.dev)
+        assert t.element_size() == 4
+        self.L.fill_u32(t.data_ptr(), 0, int(n), self.stream)
+        return t
+
+    def vec_op(self, a, b, op):
+        out = self.empty(a.numel())
+        self.L.vec_op_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), op, self.stream)
+        return out
 
     def new(self, N, H, W, C):
         return T(self.empty(N * H * W * C), N, H, W, C)
@@ -224,11 +256,13 @@ class Engine:
             out = self.new(x.N, Ho, Wo, Cout)
         assert out.C == Cout and out.H == Ho and out.W == Wo and out.N == x.N
         if self.tc_conv:
+            mode = self.conv_mode
             wp = self._wpacked.get(name)
-            if wp is None or wp[0] is not w:
-                buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, Cin, kh, kw), dtype=torch.uint8, device=self.dev)
-                self.L.conv_pack_weights_tf32x3(w.data_ptr(), Cout, Cin, kh, kw, buf.data_ptr(), self.stream)
-                wp = (w, buf)
+            if wp is None or wp[0] is not w or wp[2] != mode:
+                buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, Cin, kh, kw, mode), dtype=torch.uint8,
+                                  device=self.dev)
+                self.L.conv_pack_weights(w.data_ptr(), Cout, Cin, kh, kw, mode, buf.data_ptr(), self.stream)
+                wp = (w, buf, mode)
                 self._wpacked[name] = wp
             ts = None
             if stats:
@@ -241,7 +275,7 @@ class Engine:
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
                                   _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
                                   out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
-                                  self.conv_chunk, wsp, wsn, self.stream)
+                                  self.conv_chunk, mode, self._ovf.data_ptr(), wsp, wsn, self.stream)
             return (out, TileStats(ts, tpi, x.N, Cout)) if stats else out
         assert in_shift is None and not in_relu, "the fp32 SIMT convolution only fuses an input scale"
         self.L.conv2d_nhwc_f32(x.ptr, w.data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale), out.ptr,
@@ -411,13 +445,14 @@ class Engine:
     def _label_ids(self, mask, h, w, out=None):
         """[1,1,H,W] integer label map -> uint8 ids [h*w] (nearest resize, aocnet.py:128-135)"""
         m = mask.to(device=self.dev)
-        if m.dtype != torch.uint8:
-            m = m.clamp(0, 255).to(torch.uint8)
+        if m.dtype not in (torch.uint8, torch.int64):
+            m = m.to(torch.int64)                     # (rare: the reference hands uint8 ground truth or int64 argmax maps)
         m = m.contiguous()
         Hm, Wm = int(m.shape[-2]), int(m.shape[-1])
         if out is None:
             out = self.empty(h * w, torch.uint8)
-        self.L.resize_nearest_u8(m.data_ptr(), out.data_ptr(), Hm, Wm, h, w, self.stream)
+        fn = self.L.resize_nearest_u8 if m.dtype == torch.uint8 else self.L.resize_nearest_i64
+        fn(m.data_ptr(), out.data_ptr(), Hm, Wm, h, w, self.stream)
         return out
 
     def _sync_bank(self, ref_embeddings, ref_masks, h, w):
@@ -521,18 +556,35 @@ class Engine:
         # --- adaptive object proxies (matching.py:533-595)
         cent = self.empty(MAXO * 16 * EMB)
         labels = self.empty(max(rows, 1), torch.int32)
-        P = torch.zeros(MAXO * PROXY_SLOTS * EMB, dtype=torch.float32, device=self.dev)
-        pvalid = torch.zeros(MAXO * PROXY_SLOTS, dtype=torch.int32, device=self.dev)
+        P = self.zeros(MAXO * PROXY_SLOTS * EMB)
+        pvalid = self.zeros(MAXO * PROXY_SLOTS, torch.int32)
         kws = L.kmeans_workspace_bytes(ix["maxrows"], O)
         L.kmeans_proxies_f32(S.data_ptr(), meta.data_ptr(), ix["nat2sorted"].data_ptr(), kk_d.data_ptr(),
                              init_d.data_ptr(), O, ix["maxrows"], self.kmeans_iters, cent.data_ptr(), labels.data_ptr(),
                              P.data_ptr(), pvalid.data_ptr(), self.ws("kmeans", kws).data_ptr(), kws, st)
+        if self.force_proxies is not None:
+            self._apply_forced_proxies(P, pvalid, O)
         # --- bank attention heads / k=1 proxies (attention.py:155-189)
         hws = L.head_pool_workspace_bytes(max(total, hw))
         hbuf = self.ws("headpool", hws)
         L.head_pool_f32(bk.emb_all.data_ptr(), bk.ids_all.data_ptr(), total, O, 1e-5, head.data_ptr(), HEAD, 0, EMB,
                         P.data_ptr() + 4 * 32 * EMB, PROXY_SLOTS * EMB, hbuf.data_ptr(), hws, st)
         return g, P, pvalid, cent, labels
+
+    def _apply_forced_proxies(self, P, pvalid, O):
+        """TEST HOOK (tests/test_gpu_fullsize.py): replace the k-means proxies of this frame by given ones -- dict with
+        prox_cen / prox_avg [O,16,100] and prox_ncen / prox_navg [O] as stored by tools/make_cfg_truth.py.  k-means is a
+        discrete step (a 1e-6 change of an embedding can flip a boundary row's cluster and move the logits by 0.1), so
+        full-size logit parity is measured with both sides on the SAME proxies; the k-means kernels themselves are
+        compared bit for bit on identical inputs in tests/test_gpu_ops.py.  Plain launches only."""
+        assert not torch.cuda.is_current_stream_capturing(), "force_proxies needs AOCB200_GRAPHS=0 / use_graphs = False"
+        f = self.force_proxies
+        Pv, vv = P.view(MAXO, PROXY_SLOTS, EMB), pvalid.view(MAXO, PROXY_SLOTS)
+        ar = torch.arange(16, device=self.dev).view(1, 16)
+        for key, cnt, lo in (("prox_cen", "prox_ncen", 0), ("prox_avg", "prox_navg", 16)):
+            Pv[:O, lo:lo + 16] = torch.as_tensor(f[key], dtype=torch.float32, device=self.dev)
+            n = torch.as_tensor(f[cnt], dtype=torch.int32, device=self.dev).view(O, 1)
+            vv[:O, lo:lo + 16] = (ar < n).to(torch.int32)
 
     def _match_back(self, q, g, P, pvalid, head, prev_e, prev_ids, O):
         """bank-independent part: previous-frame heads, cluster/proxy matching, local matching, pre-head.
@@ -559,7 +611,7 @@ class Engine:
         x2, y2 = self.empty(hh * ww), self.empty(hh * ww)
         L.row_sqnorm_f32(xq.ptr, hh * ww, x2.data_ptr(), st)
         L.row_sqnorm_f32(yp.ptr, hh * ww, y2.data_ptr(), st)
-        loc_lr = T(torch.zeros(hh * ww * ldl, dtype=torch.float32, device=self.dev), 1, hh, ww, ldl)
+        loc_lr = T(self.zeros(hh * ww * ldl), 1, hh, ww, ldl)
         L.local_match_f32(xq.ptr, yp.ptr, x2.data_ptr(), y2.data_ptr(), ids_lr.data_ptr(), hh, ww, O, bias.data_ptr(),
                           loc_lr.ptr, ldl, st)
         loc = self.resize_bilinear(loc_lr, h, w)
@@ -568,7 +620,7 @@ class Engine:
         L.resize_bilinear_nhwc_f32(None, prev_ids.data_ptr(), prev_pos.data_ptr(), O, yq.ptr, 1, h, w, hh, ww, EMB, EMB,
                                    EMB, st)
         L.row_sqnorm_f32(yq.ptr, hh * ww, y2.data_ptr(), st)
-        locp_lr = T(torch.zeros(hh * ww * ldl, dtype=torch.float32, device=self.dev), 1, hh, ww, ldl)
+        locp_lr = T(self.zeros(hh * ww * ldl), 1, hh, ww, ldl)
         L.local_match_f32(xq.ptr, yq.ptr, x2.data_ptr(), y2.data_ptr(), ids_lr.data_ptr(), hh, ww, O, bias.data_ptr(),
                           locp_lr.ptr, ldl, st)
         locp = self.resize_bilinear(locp_lr, h, w)
@@ -643,7 +695,7 @@ class Engine:
             r, sr = self.conv(x, p + ".downsample.0", stride=stride, in_scale=pre, stats=True)
             ar, br = self.gn_ab(r, p + ".downsample.1", 32, sr)
             # relu(GN3(y3) + GN_ds(r)) = relu(y3*a3 + (b3 + br) + r*ar)
-            return self.affine(y3, a3, b3 + br, res=r, res_scale=ar, relu=True, want_stats=want_stats)
+            return self.affine(y3, a3, self.vec_op(b3, br, 0), res=r, res_scale=ar, relu=True, want_stats=want_stats)
         return self.affine(y3, a3, b3, res=x, res_scale=pre, relu=True, want_stats=want_stats)
 
     def cond_scale(self, x, p, beta=0.3):
@@ -685,7 +737,7 @@ class Engine:
             y, s_y = self.conv(x, q + ".atrous_conv", pad=d, dil=max(d, 1), in_scale=gate, stats=True)
             self.gn(y, q + ".bn", 32, relu=True, out=cat.slice(128 * (i - 1), 128), st=s_y)
         gp = self.gap(x, st)
-        g = T(gp if pre is None else gp * pre, O, 1, 1, x.C)
+        g = T(gp if pre is None else self.vec_op(gp, pre, 1), O, 1, 1, x.C)
         g = self.conv(g, p + ".global_avg_pool.1", relu=True)
         self.resize_bilinear(g, x.H, x.W, out=cat.slice(512, 128))
         gate = self.gct_gate(cat, p + ".GCT")
@@ -770,14 +822,24 @@ class Engine:
     def _num_objects(self, gt_ids):
         if isinstance(gt_ids, int):
             return gt_ids
-        key = (id(gt_ids), getattr(gt_ids, "_version", 0))
-        if self._gt_cache[0] != key:                      # a device tensor costs one D2H sync; once per sequence
-            self._gt_cache = (key, int(gt_ids[0]))
-        return self._gt_cache[1]
+        # A device tensor costs one D2H sync: read once per tensor OBJECT (held strongly, so its identity cannot be
+        # recycled by the allocator) and version; a caller that builds a fresh tensor per frame pays the read per frame,
+        # DeviceSequence passes a Python int.
+        t, ver, k = self._gt_cache
+        if t is not gt_ids or ver != getattr(gt_ids, "_version", 0):
+            k = int(gt_ids[0]) if hasattr(gt_ids, "__getitem__") else int(gt_ids)
+            self._gt_cache = (gt_ids, getattr(gt_ids, "_version", 0), k)
+        return k
 
     def set_seen_labels(self, labels=None):
         """Labels that appeared in a ground-truth frame of this sequence so far (`label_all_list`,
-        eval_manager_mm.py:262-265); None = every slot.  Probabilities of the other slots come back as zeros."""
+        eval_manager_mm.py:262-265); None = every slot.  Shapes only `last_label` / `last_conf_label` (the argmax and
+        the confident mask over the seen slots); the probabilities forward_for_eval returns are always the reference's
+        plain softmax, so a sequence driver that sets this (DeviceSequence) cannot change what another caller gets."""
+        self._set_exist_bits(self.seen_bits(labels))
+
+    @staticmethod
+    def seen_bits(labels):
         bits = -1
         if labels is not None:
             bits = 0
@@ -785,18 +847,94 @@ class Engine:
                 if 0 <= int(v) < MAXO:
                     bits |= 1 << int(v)
             bits -= (1 << 32) if bits >= (1 << 31) else 0
-        self._exist.copy_(torch.tensor([bits], dtype=torch.int32))    # pageable source: staged before the call returns
+        return bits
+
+    def _set_exist_bits(self, bits):
+        if bits != self._exist_bits:
+            self._exist.copy_(torch.tensor([bits], dtype=torch.int32))    # pageable source: staged before the call returns
+            self._exist_bits = bits
 
     def _upsample_softmax(self, logits, O, h, w, H, W):
-        probs = torch.empty((1, O, H, W), dtype=torch.float32, device=self.dev)
+        """aocnet.py:100-107 -> probs (the plain softmax the reference returns; None when `want_probs` is off), plus the
+        eval loop's derived maps: label = argmax over the seen slots, conf = label or 125 (see set_seen_labels)"""
+        probs = torch.empty((1, O, H, W), dtype=torch.float32, device=self.dev) if self.want_probs else None
         label = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
         conf = torch.empty((H, W), dtype=torch.uint8, device=self.dev)
-        self.L.upsample_softmax_label_f32(logits.data_ptr(), probs.data_ptr(), label.data_ptr(), conf.data_ptr(), None,
+        self.L.upsample_softmax_label_f32(logits.data_ptr(), _p(probs), label.data_ptr(), conf.data_ptr(), None,
                                           self._exist.data_ptr(), float(self.unc_ratio), O, h, w, H, W, self.stream)
         return probs, label, conf
 
+    # ------------------------------------------------------------------ fp16 operand range guard
+    # The split-fp16 convolution clamps |x| at 65504.  Every convolution launch ORs "an operand reached 6e4" into the
+    # device word `_ovf`; after each frame the word is copied to pinned host memory behind an event.
+    #   sync      wait for the frame, and if the word is set: switch this engine to 3xTF32 operands, restore numpy's RNG
+    #             state (the k-means draws of the frame), run the frame again, warn.  Costs one host wait per frame.
+    #   deferred  (default) never waits: the word of frame t is looked at when a later call finds its event complete; a
+    #             set word raises AocError naming the frame (its outputs, already handed out, are invalid) after
+    #             switching the engine to 3xTF32, so the caller can repeat the sequence.
+    #   off       no check.
+    def _overflow_trip(self, frame, rerun):
+        import warnings
+        from .lib import AocError
+        torch.cuda.synchronize(self.dev)
+        self.overflow_frames.append(frame)
+        self.conv_mode = 0
+        self.L.fill_u32(self._ovf.data_ptr(), 0, 1, self.stream)
+        self._segA.clear(); self._static.clear()            # graphs captured with split-fp16 kernels / weight images
+        for slot in self._ovf_ring:
+            slot[2][0] = None
+        msg = ("aocb200: a convolution input of frame %d reached the fp16 range (|x| >= 6e4); the split-fp16 operand "
+               "mode would have clamped it.  This engine now uses 3xTF32 operands (fp32 range, ~12 %% slower)." % frame)
+        if rerun:
+            warnings.warn(msg + "  The frame was run again.", RuntimeWarning)
+        else:
+            raise AocError(msg + "  Outputs returned for that frame (and later ones) are invalid: repeat the sequence, "
+                           "or set AOCB200_OVERFLOW=sync for transparent re-runs.")
+
+    def _overflow_poll(self, block=False):
+        for host, ev, tag in self._ovf_ring:
+            if tag[0] is not None and (block or ev.query()):
+                if block:
+                    ev.synchronize()
+                frame, tag[0] = tag[0], None
+                if int(host[0]) != 0:
+                    self._overflow_trip(frame, rerun=False)
+
     def forward_for_eval(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
                          pred_size, gt_ids):
+        pol = self.overflow_policy if (self.tc_conv and self.conv_mode == 1) else "off"
+        if pol == "off":
+            self.frame_no += 1
+            return self._forward(memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
+                                 pred_size, gt_ids)
+        self._overflow_poll()
+        rng = np.random.get_state() if pol == "sync" else None
+        out = self._forward(memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
+                            pred_size, gt_ids)
+        frame = self.frame_no
+        self.frame_no += 1
+        host, ev, tag = self._ovf_ring[self._ovf_turn % len(self._ovf_ring)]
+        self._ovf_turn += 1
+        if tag[0] is not None:                               # slot still carries an unchecked frame: check it first
+            ev.synchronize()
+            old, tag[0] = tag[0], None
+            if int(host[0]) != 0:
+                self._overflow_trip(old, rerun=False)
+        host.copy_(self._ovf, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.dev))
+        tag[0] = frame
+        if pol == "sync":
+            ev.synchronize()
+            tag[0] = None
+            if int(host[0]) != 0:
+                self._overflow_trip(frame, rerun=True)
+                np.random.set_state(rng)
+                return self._forward(memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask,
+                                     current_frame, pred_size, gt_ids)
+        return out
+
+    def _forward(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
+                 pred_size, gt_ids):
         if self.use_graphs and not self.keep_debug:
             return self._forward_graphed(memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask,
                                          current_frame, pred_size, gt_ids)
@@ -938,7 +1076,7 @@ class Engine:
                 st["segF"] = segF
             segF["graph"].replay()
         # ---- segment C: everything after the bank
-        keyC = (Hp, Wp, has[0], has[1], id(emb), float(self.unc_ratio))
+        keyC = (Hp, Wp, has[0], has[1], id(emb), float(self.unc_ratio), bool(self.want_probs))
         segC = st["segC"].get(keyC)
         if segC is None:
             back()                                           # warm-up
@@ -950,4 +1088,5 @@ class Engine:
         self.last_logits = logits.view(1, O, h, w)
         self.last_label, self.last_conf_label = label, conf      # static buffers of the graph: clone to keep
         cl = torch.channels_last
-        return probs.clone(), emb_out, [[mem[0].nchw().clone(memory_format=cl), mem[1].nchw().clone(memory_format=cl)]]
+        return (None if probs is None else probs.clone()), emb_out, \
+            [[mem[0].nchw().clone(memory_format=cl), mem[1].nchw().clone(memory_format=cl)]]

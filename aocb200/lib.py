@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libaocb200%s.so" % ("_" + _TAG if _TAG else ""))
 
 _CT = {
     "int": ctypes.c_int, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong,
-    "cudaStream_t": ctypes.c_void_p,
+    "cudaStream_t": ctypes.c_void_p, "unsigned int": ctypes.c_uint,
 }
 
 

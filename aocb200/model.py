@@ -22,6 +22,8 @@ class AOCNetB200(ParamTree):
         super().__init__()
         self.cfg = cfg
         self._engine = None
+        self._fx = feature_extracter      # kept for forward() (training), which delegates to the reference module
+        self._ref = None
         if isinstance(feature_extracter, torch.nn.Module):
             sd = {"feature_extracter." + k: v for k, v in feature_extracter.state_dict().items()}
             own = self.state_dict()
@@ -64,8 +66,31 @@ class AOCNetB200(ParamTree):
 
     def forward(self, input, memory_prev_list=None, ref_frame_label=None, previous_frame_mask=None,
                 current_frame_mask=None, gt_ids=None, step=0, tf_board=False):
-        """aocnet.py:54-82 is the training forward (loss + boards); training is outside this inference engine."""
-        raise NotImplementedError("aocb200 accelerates forward_for_eval (inference) only; train with the reference")
+        """aocnet.py:54-82 is the TRAINING forward (loss + boards).  Training is outside this inference engine, so the
+        call is delegated to the reference's own torch module: it is built on first use from the
+        reference package on sys.path (`networks.aoc.aocnet`, or cfg.MODEL_REFERENCE_MODULE), around the
+        `feature_extracter` this object was constructed with, and SHARES this module's parameter tensors
+        (load_state_dict(assign=True)), so an optimiser stepping either side updates both.  Without the reference
+        package there is nothing to delegate to and the call raises."""
+        return self._reference_module()(input, memory_prev_list, ref_frame_label, previous_frame_mask,
+                                        current_frame_mask, gt_ids, step=step, tf_board=tf_board)
+
+    def _reference_module(self):
+        if self._ref is None:
+            import importlib
+            name = getattr(self.cfg, "MODEL_REFERENCE_MODULE", "networks.aoc.aocnet")
+            try:
+                mod = importlib.import_module(name)
+            except ImportError as e:
+                raise NotImplementedError(
+                    "AOCNetB200.forward (training) delegates to the reference's torch module '%s', which is not "
+                    "importable here (%s); aocb200 itself accelerates forward_for_eval only" % (name, e)) from e
+            if not isinstance(self._fx, torch.nn.Module):
+                raise NotImplementedError("AOCNetB200.forward needs the feature_extracter module it was constructed with")
+            ref = mod.get_module()(self.cfg, self._fx)
+            ref.load_state_dict(self.state_dict(keep_vars=True), strict=False, assign=True)
+            self._ref = ref
+        return self._ref
 
 
 def get_module():

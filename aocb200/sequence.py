@@ -78,26 +78,42 @@ class DeviceSequence:
     are uint8 device tensors, the label-existence filter (eval_manager_mm.py:252-270), the argmax (:318-320) and the
     entropy -> label-125 "confident" mask (:339-349, shannon_entropy.py:10-13) come out of the engine's fused
     upsample + softmax kernel (`aoc_upsample_softmax_label_f32`), so a predicted frame adds no torch kernels and
-    no host read-back to `forward_for_eval`.  CUDA engine only (`model.engine()`); no fallback."""
+    no host read-back to `forward_for_eval`.  CUDA engine only (`model.engine()`); no fallback.
+    The sequence's settings (seen-label word, entropy threshold, probability output off unless `keep_probs`) are applied
+    to the engine for the duration of each step() and undone afterwards: plain `forward_for_eval` callers and other
+    sequences sharing the model never see them."""
 
-    def __init__(self, model, num_objects, mem_every=5, unc_ratio=1.0, device=None):
+    def __init__(self, model, num_objects, mem_every=5, unc_ratio=1.0, device=None, keep_probs=False):
         self.m, self.eng = model, model.engine()
         self.dev = device if device is not None else self.eng.dev
         self.K, self.mem_every = int(num_objects), int(mem_every)
-        self.eng.unc_ratio = float(unc_ratio)
-        self.eng.set_seen_labels(None)                                          # reset; the first ground-truth frame sets the list
-        self.gt_ids = torch.tensor([self.K], device=self.dev)
+        self.unc_ratio, self.keep_probs = float(unc_ratio), bool(keep_probs)
+        self.gt_ids = self.K                                                    # a Python int: no device read per frame
         self.ref_e, self.ref_m = [], []
         self.prev_e = self.prev_m = None
         self.memory = [[None, None]]
         self.seen = set()
+        self.bits = 0                                                           # set by the first ground-truth frame
+        self.probs = None
         self.t = -1
 
     def _see(self, label):
         new = set(int(v) for v in torch.unique(label).tolist()) - self.seen      # GT frames only: one small read-back
         if new:
             self.seen |= new
-            self.eng.set_seen_labels(self.seen)
+            self.bits = self.eng.seen_bits(self.seen)
+
+    def _forward(self, img):
+        eng = self.eng
+        saved = (eng.unc_ratio, eng.want_probs)
+        eng.unc_ratio, eng.want_probs = self.unc_ratio, self.keep_probs
+        eng._set_exist_bits(self.bits)
+        try:
+            return self.m.forward_for_eval(self.memory, self.ref_e, self.ref_m, self.prev_e, self.prev_m, img,
+                                           pred_size=[int(img.shape[-2]), int(img.shape[-1])], gt_ids=self.gt_ids)
+        finally:
+            eng.unc_ratio, eng.want_probs = saved
+            eng._set_exist_bits(-1)
 
     def step(self, img, gt_label=None):
         """img [1,3,H,W] normalised frame (device or pinned host); gt_label [H,W] ints if this frame carries ground
@@ -110,8 +126,7 @@ class DeviceSequence:
             gt_label = gt_label.to(self.dev).to(torch.uint8).view(H, W)
             if t == 0:
                 self._see(gt_label)
-        probs, emb, self.memory = self.m.forward_for_eval(self.memory, self.ref_e, self.ref_m, self.prev_e, self.prev_m,
-                                                          img, pred_size=[H, W], gt_ids=self.gt_ids)
+        probs, emb, self.memory = self._forward(img)
         if t == 0:
             assert gt_label is not None, "the first frame carries the ground-truth label"
             lab = gt_label.view(1, 1, H, W)

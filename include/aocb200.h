@@ -47,9 +47,12 @@ int aoc_version(void);
 const char* aoc_last_error_string(void);
 /* 0 if device `dev` can run this library (compute capability 10.x), else AOC_EARCH / AOC_ELAUNCH. */
 int aoc_check_device(int dev);
-/* tuning / diagnostic switches.  "conv_chunk" (default 8): default length, in 16-channel stages, of the TMEM
- * accumulation chains of the tensor-core convolution (see aoc_conv2d_nhwc_tc).  "conv_splitk" (default 1): allow the
- * split-K schedule for layers with few output tiles. */
+/* Tuning / diagnostic switches for tests and tools -- the ONE piece of process-global mutable state in the library
+ * (everything that selects arithmetic on the product path is a per-call argument).  "conv_chunk" (default 8): default
+ * length, in 16-channel stages, of the TMEM accumulation chains of the tensor-core convolution (see
+ * aoc_conv2d_nhwc_tc).  "conv_splitk" (default 1): allow the split-K schedule for layers with few output tiles.
+ * "conv_pdl" (default 1): programmatic dependent launch.  "match_f16" (default 1): split-fp16 operands in the matching
+ * contraction (0 = 3xTF32). */
 int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */
@@ -60,20 +63,29 @@ int aoc_set_option(const char* key, int value);
 int aoc_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, const float* residual,
                         const float* in_scale, float* y, int N, int H, int W, int Cin, int ldx, int Cout, int ldy,
                         int ldres, int kh, int kw, int stride, int pad, int dil, int relu, cudaStream_t stream);
-/* Same contract on the tcgen05 tensor cores (csrc/umma_conv2.cu): 3xTF32 split operands, fp32 accumulate in TMEM in
- * chains of `chunk_stages` x 16 input channels that are summed in fp32 registers (round to nearest), so the result
- * has fp32-FMA quality for any K.  The activation patch is fetched by TMA (zero fill = padding) and the
- * per-(sample, channel) affine that precedes the convolution in the reference is fused into the operand path:
+/* Same contract on the tcgen05 tensor cores (csrc/umma_conv2.cu).  fp32 products are rebuilt from two-term operand
+ * splits (22 mantissa bits, the lo*lo term dropped), selected per call by `operand_mode`:
+ *     AOC_CONV_SPLIT_F16  hi = fp16(x), lo = fp16((x - hi) * 2^11): three K = 16 kind::f16 MMAs per 16 channels.
+ *                         Range: |x|, |w| saturate at 65504; `overflow_flag` (optional device word) is set to 1 when an
+ *                         activation operand reaches 6e4, so the caller can repeat the frame in the other mode.
+ *     AOC_CONV_TF32X3     hi = rna_tf32(x), lo = rna_tf32(x - hi): six K = 8 kind::tf32 MMAs; fp32 exponent range.
+ * fp32 accumulation in TMEM in chains of `chunk_stages` x 16 input channels that are summed in fp32 registers (round to
+ * nearest), so the result has fp32-FMA quality for any K.  The activation patch is fetched by TMA (zero fill =
+ * padding) and the per-(sample, channel) affine that precedes the convolution in the reference is fused into the
+ * operand path:
  *     x_eff = relu?(x * in_a[n,c] + in_b[n,c])      (GroupNorm apply + ReLU, GCT gate, IA gate; each optional)
- * w_packed comes from aoc_conv_pack_weights_tf32x3 (size aoc_conv_packed_weight_bytes).  Requires ldx % 4 == 0,
- * stride in {1, 2}; Cin <= 1024 when an input affine is given.  chunk_stages <= 0 selects the default (8). */
-size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw);
-int aoc_conv_pack_weights_tf32x3(const float* w, int Cout, int Cin, int kh, int kw, void* w_packed,
-                                 cudaStream_t stream);
+ * w_packed comes from aoc_conv_pack_weights with the SAME operand_mode (size aoc_conv_packed_weight_bytes).  Requires
+ * ldx % 4 == 0, stride in {1, 2}; Cin <= 1024 when an input affine is given.  chunk_stages <= 0 selects the default (8). */
+#define AOC_CONV_TF32X3 0
+#define AOC_CONV_SPLIT_F16 1
+size_t aoc_conv_packed_weight_bytes(int Cout, int Cin, int kh, int kw, int operand_mode);
+int aoc_conv_pack_weights(const float* w, int Cout, int Cin, int kh, int kw, int operand_mode, void* w_packed,
+                          cudaStream_t stream);
 int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
                        const float* in_a, const float* in_b, int in_relu, float* y, float* tile_stats, int N, int H,
                        int W, int Cin, int ldx, int Cout, int ldy, int ldres, int kh, int kw, int stride, int pad,
-                       int dil, int relu, int chunk_stages, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                       int dil, int relu, int chunk_stages, int operand_mode, int* overflow_flag, void* workspace,
+                       size_t ws_bytes, cudaStream_t stream);
 /* workspace (optional, aoc_conv_workspace_bytes): partial sums for split-K, used when the layer has too few output
  * tiles to fill the chip (the 31x54 maps of the backbone); without it such layers run unsplit. */
 size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
@@ -145,6 +157,12 @@ int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi,
 int aoc_copy_channels_f32(const float* x, float* y, long long rows, int C, int ldx, int ldy, cudaStream_t stream);
 /* F.interpolate(mode='nearest') on label maps (aocnet.py:128-135) */
 int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
+/* the same for an int64 label map (torch.argmax output, eval_manager_mm.py:318-320), values clamped to 0..255 */
+int aoc_resize_nearest_i64(const long long* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
+/* plumbing that would otherwise be eager torch kernels inside the captured frame: fill n 32-bit words; out = a + b
+ * (op 0) or a * b (op 1) over n floats (sums / products of per-(sample, channel) coefficient vectors) */
+int aoc_fill_u32(void* p, unsigned int value, long long n_words, cudaStream_t stream);
+int aoc_vec_op_f32(const float* a, const float* b, float* out, int n, int op, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- reference bank (matching.cu) */
 size_t aoc_bank_workspace_bytes(int total_pixels, int O);
@@ -206,9 +224,11 @@ int aoc_upsample_softmax_f32(const float* logits, float* probs, uint8_t* label, 
 /* The same upsample + softmax with the eval loop's per-frame label bookkeeping fused behind it (SURVEY 8f rows 1-2;
  * eval_manager_mm.py:252-270 "delete the label that hasn't existed in the GT label", :318-320 argmax, :339-349
  * uncertainty region filter; layers/shannon_entropy.py:10-13).  exist_bits: device int32 word, bit o set <=> label o
- * was seen in a ground-truth frame so far (NULL = every slot); probs[o] of an unseen slot is 0; label = argmax of the
- * filtered probs (uint8, lowest index on ties); conf_label (optional) = 125 where the entropy over the seen slots
- * exceeds unc_ratio, else label -- the "confident" mask the memory bank stores; entropy (optional) [H][W] floats. */
+ * was seen in a ground-truth frame so far (NULL = every slot).  probs (optional) is always the plain softmax that
+ * AOCNet.forward_for_eval returns (aocnet.py:100-107) -- the filter is the CALLER's bookkeeping and only shapes the
+ * derived maps: label = argmax over the seen slots (uint8, lowest index on ties; == argmax of probs * keep);
+ * conf_label (optional) = 125 where the entropy over the seen slots exceeds unc_ratio, else label -- the "confident"
+ * mask the memory bank stores; entropy (optional) [H][W] floats. */
 int aoc_upsample_softmax_label_f32(const float* logits, float* probs, uint8_t* label, uint8_t* conf_label,
                                    float* entropy, const int* exist_bits, float unc_ratio, int O, int h, int w, int H,
                                    int W, cudaStream_t stream);

@@ -236,18 +236,26 @@ def global_matching_for_eval(ref_embs, q, ref_onehots, dis_bias):
         return torch.ones(h, w, O)
     e, l = bank
     qf = q.reshape(-1, C)
-    d = _pairwise(qf, qf.pow(2).sum(1), e, e.pow(2).sum(1))  # [hw, N]
-    feats = []
-    for o in range(O):
-        # matching.py:83-90: min_n (d + 5e4*[label_n != o]); fp add is monotone so the min splits.
-        right = l[:, o] > 0.1
-        cand = []
-        if bool(right.any()):
-            cand.append(d[:, right].min(1)[0])
-        if bool((~right).any()):
-            cand.append(d[:, ~right].min(1)[0] + WRONG_LABEL_PADDING_DISTANCE)
-        feats.append(cand[0] if len(cand) == 1 else torch.minimum(cand[0], cand[1]))
-    feats = torch.stack(feats, 1).view(h, w, O)
+    q2, e2 = qf.pow(2).sum(1), e.pow(2).sum(1)
+    # matching.py:200-249 walks the query pixels in chunks (rows are independent); here the chunk only bounds the
+    # [chunk, N] distance block to ~1 Gi elements -- the golden-fixture sizes are a single chunk
+    step = max(1, min(qf.shape[0], (1 << 30) // max(1, e.shape[0])))
+    rows = []
+    for c0 in range(0, qf.shape[0], step):
+        d = _pairwise(qf[c0:c0 + step], q2[c0:c0 + step], e, e2)  # [chunk, N]
+        feats = []
+        for o in range(O):
+            # matching.py:83-90: min_n (d + 5e4*[label_n != o]); fp add is monotone so the min splits.
+            right = l[:, o] > 0.1
+            cand = []
+            if bool(right.any()):
+                cand.append(d[:, right].min(1)[0])
+            if bool((~right).any()):
+                cand.append(d[:, ~right].min(1)[0] + WRONG_LABEL_PADDING_DISTANCE)
+            feats.append(cand[0] if len(cand) == 1 else torch.minimum(cand[0], cand[1]))
+        rows.append(torch.stack(feats, 1))
+        del d
+    feats = torch.cat(rows, 0).view(h, w, O)
     return _sig(feats, dis_bias.view(1, 1, -1))
 
 

@@ -59,3 +59,33 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), fn
+
+
+def test_state_dict_names_match_reference():
+    """tests/golden/state_dict_keys.json was dumped from the reference's own module tree (tools/make_golden.py): names,
+    shapes and registration order of AOCNet.state_dict() -- what load_network (utils/checkpoint.py:49-70) matches on."""
+    import json
+    import os
+    from aocb200.model import get_module
+    from aocb200.params import param_spec
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")))
+    ref = ref["keys"] if isinstance(ref, dict) and "keys" in ref else ref
+    ref = [(k, tuple(v)) for k, v in (ref.items() if isinstance(ref, dict) else ref)]
+    spec = [(k, tuple(shape)) for k, (_, shape) in param_spec().items()]
+    assert spec == ref, "param_spec() differs from the reference's state_dict (first diff: %s)" % next(
+        ((a, b) for a, b in zip(spec, ref) if a != b), (len(spec), len(ref)))
+    # the module tree registers the `semantic_embedding` alias last; load_state_dict matches by NAME, so the module is
+    # held to the same names and shapes, param_spec() above also to the reference's order
+    own = get_module()(None, None).state_dict()
+    assert sorted((k, tuple(v.shape)) for k, v in own.items()) == sorted(ref)
+
+
+def test_forward_delegates_or_explains():
+    """forward() (training, aocnet.py:54-82) is delegated to the reference's torch module; where that package is not
+    importable the error says so -- it is not a silent no-op."""
+    import torch
+    from aocb200.model import get_module
+    m = get_module()(None, None)
+    with pytest.raises(NotImplementedError) as e:
+        m.forward(torch.zeros(1, 3, 33, 33))
+    assert "reference" in str(e.value)

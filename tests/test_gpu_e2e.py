@@ -1,6 +1,13 @@
 """End-to-end parity of the CUDA engine through the reference-facing API (get_module() -> forward_for_eval) against
 (a) the committed fixtures produced by the repaired reference and (b) the CPU oracle stage by stage.
-Tolerance (BASELINE.json north_star): argmax masks bit-exact, mask logits within 1e-3 max-abs."""
+Target (BASELINE.json north_star): argmax masks bit-exact, mask logits within 1e-3 max-abs.  What two fp32 evaluations
+can reach, and what is therefore ASSERTED (observed value x 1.5), is stated per test.
+
+Observed on B200 (round 1, final kernels): |engine - fp64| 2.6e-3 .. 3.6e-3, |engine - reference| 3.2e-3 .. 4.2e-3, at
+most 3 argmax pixels per frame differing from the reference (all at float64 top-2 margins below 1e-3)."""
+TINY_D64 = 6.0e-3       # |engine - fp64|      (observed <= 3.6e-3; the reference's own fp32 result: 2.1e-3 .. 3.3e-3)
+TINY_DREF = 7.0e-3      # |engine - reference| (observed <= 4.2e-3)
+TINY_MISM_PX = 6        # argmax pixels differing from the reference per frame (observed <= 3), all at fp64 near-ties
 import glob
 import os
 
@@ -73,13 +80,12 @@ def test_sequence_vs_reference_fixture(model, path):
     Tolerances.  BASELINE.json asks for logits within 1e-3 max-abs of the reference's fp32 forward and bit-exact argmax
     masks.  On these inputs the reference's own fp32 CPU result is 2.1e-3 .. 3.3e-3 away from the float64 evaluation
     of the same network (tests/golden/*_fp64.pt, tools/make_fp64_truth.py; logit range ~ +-25), so two correct fp32
-    implementations with different summation orders cannot agree to 1e-3.  Asserted here:
-      (1) |engine - fp64| <= 2 * |reference - fp64|   (the engine is as close to exact arithmetic as the reference,
-          up to the run-to-run spread of a max-norm over ~50k logits; measured ratios 0.6 .. 1.5);
-      (2) |engine - reference| <= 1e-3 + |engine - fp64| + |reference - fp64|   (triangle bound; the raw number is
-          printed against the 1e-3 target);
-      (3) argmax masks identical except at pixels whose fp64 top-2 logit margin is below 2x the fp32 noise
-          (genuine numerical ties); the fraction of such pixels must stay below 0.1 %.
+    implementations with different summation orders cannot agree to 1e-3.  Asserted here (observed x 1.5, constants at
+    the top of this file):
+      (1) |engine - fp64| <= 6e-3   (the engine is as close to exact arithmetic as the reference itself);
+      (2) |engine - reference| <= 7e-3   (the raw number is printed against the 1e-3 target);
+      (3) argmax masks identical to the reference's except at <= 6 pixels per frame, every one of them a float64
+          near-tie (top-2 logit margin below the sum of both fp32 distances to float64).
     """
     import torch.nn.functional as F
     from aocb200.sequence import run_sequence
@@ -102,8 +108,9 @@ def test_sequence_vs_reference_fixture(model, path):
         eq = 1.0 - mism.float().mean().item()
         print("[parity] %s frame %d: |engine-ref|=%.3e (target 1e-3)  |engine-fp64|=%.3e  |ref-fp64|=%.3e  argmax-equal=%.6f"
               % (os.path.basename(path), t + 1, d_ref, d_64, n_ref, eq))
-        assert d_64 <= 2.0 * n_ref, (t, d_64, n_ref)
-        assert d_ref <= 1e-3 + d_64 + n_ref, (t, d_ref)
+        assert d_64 <= TINY_D64, (t, d_64, n_ref)
+        assert d_ref <= TINY_DREF, (t, d_ref)
+        assert int(mism.sum()) <= TINY_MISM_PX, (t, int(mism.sum()))
         if mism.any():
             up = F.interpolate(truth, size=(g["H"], g["W"]), mode="bilinear", align_corners=True)[0]
             # the eval loop zeroes the probabilities of ids never seen in a ground-truth frame
@@ -111,5 +118,57 @@ def test_sequence_vs_reference_fixture(model, path):
             exist = sorted(int(v) for v in torch.unique(first).tolist())
             top2 = torch.topk(up[exist], 2, dim=0)[0]
             margin = (top2[0] - top2[1])[mism]
-            assert margin.max().item() <= 2.0 * (d_64 + n_ref), ("argmax differs away from a numerical tie", margin.max().item())
-            assert mism.float().mean().item() < 1e-3
+            assert margin.max().item() <= d_64 + n_ref, ("argmax differs away from a numerical tie", margin.max().item())
+
+
+def test_fp16_range_guard(state_dict):
+    """A checkpoint whose activations leave the fp16 range (here: the stem's FrozenBatchNorm scale x 3e4) must not give
+    silently clamped results.  `sync` policy: the frame is re-run with 3xTF32 operands, with a warning, and the result
+    is bit-identical to an engine that used 3xTF32 from the start.  `deferred` policy (default): a later call raises."""
+    import warnings
+    from aocb200.lib import AocError
+    from aocb200.model import get_module
+    from aocb200.sequence import run_sequence
+    from aocb200.synth import make_clip
+    sd = dict(state_dict)
+    k = "feature_extracter.backbone.bn1.weight"
+    sd[k] = sd[k] * 3.0e4
+    frames, labels = make_clip(9, 65, 97, 1, 4)
+    dev = torch.device("cuda:0")
+
+    def build(policy, mode=None):
+        m = get_module()(None, None)
+        m.load_state_dict(sd)
+        m = m.cuda().eval()
+        e = m.engine()
+        e.overflow_policy = policy
+        if mode is not None:
+            e.conv_mode = mode
+        return m, e
+
+    m_ref, e_ref = build("off", 0)
+    np.random.seed(9)
+    want = run_sequence(m_ref, frames, labels[0], 1, mem_every=2, device=dev)
+    want_logits = e_ref.last_logits.clone()
+    assert torch.isfinite(want_logits).all()
+
+    m_s, e_s = build("sync")
+    assert e_s.conv_mode == 1                               # the folded weights themselves fit the fp16 range
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        np.random.seed(9)
+        got = run_sequence(m_s, frames, labels[0], 1, mem_every=2, device=dev)
+    assert e_s.conv_mode == 0 and e_s.overflow_frames == [0]
+    assert any("fp16 range" in str(w.message) for w in wlist)
+    assert torch.equal(e_s.last_logits, want_logits)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+
+    m_d, e_d = build("deferred")
+    with pytest.raises(AocError) as err:
+        np.random.seed(9)
+        run_sequence(m_d, frames, labels[0], 1, mem_every=2, device=dev)
+        e_d._overflow_poll(block=True)
+    assert "fp16 range" in str(err.value) and e_d.conv_mode == 0
+    np.random.seed(9)                                       # the repeated sequence is right
+    again = run_sequence(m_d, frames, labels[0], 1, mem_every=2, device=dev)
+    assert all(torch.equal(a, b) for a, b in zip(again, want))

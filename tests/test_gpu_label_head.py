@@ -43,9 +43,9 @@ def test_upsample_softmax_label(model, O, h, w, H, W, seen, thr):
     ex = list(range(O)) if seen is None else seen
     keep = torch.zeros(O, device="cuda")
     keep[ex] = 1.0
-    p_exist, p = p[:, ex], p * keep.view(1, -1, 1, 1)
-    assert (probs - p).abs().max().item() < 2e-6
-    assert (probs[:, [o for o in range(O) if o not in ex]] == 0).all()
+    assert (probs - p).abs().max().item() < 2e-6    # the probabilities are the reference's plain softmax (aocnet.py:100-107)
+    assert (probs.sum(1) - 1.0).abs().max().item() < 1e-5
+    p_exist, p = p[:, ex], p * keep.view(1, -1, 1, 1)     # the filter shapes only the derived label maps
     want = torch.argmax(p[0], dim=0)
     mism = label.long() != want
     if mism.any():                                  # only at numerical ties of the two largest probabilities
@@ -80,8 +80,8 @@ def test_device_sequence_vs_eval_loop(model, later):
                                 later_labels=join)
     np.random.seed(5)
     got = run_sequence_device(model, frames, first, K, mem_every=2, unc_ratio=0.3, later_labels=join)
-    model.engine().set_seen_labels(None)
-    model.engine().unc_ratio = 1.0
+    eng = model.engine()
+    assert eng._exist_bits == -1 and eng.unc_ratio == 1.0 and eng.want_probs      # the sequence's settings did not leak
     assert len(got) == len(want) == T - 1
     for t, (a, b) in enumerate(zip(got, want)):
         assert a.dtype == torch.uint8 and a.is_cuda
@@ -91,3 +91,58 @@ def test_device_sequence_vs_eval_loop(model, later):
     assert (wprobs[0][:, 2] == 0).all()             # the absent id never wins before it has been seen
     if later:
         assert (got[-1] == 2).any()                 # and is tracked once it has joined
+
+
+def test_plain_forward_after_device_sequence(model):
+    """A DeviceSequence with a label filter must not change what a later plain forward_for_eval caller gets: the
+    probabilities stay the reference's softmax over ALL slots (they sum to 1; aocnet.py:100-107)."""
+    from aocb200.sequence import run_sequence, run_sequence_device
+    from aocb200.synth import make_clip
+    K = 3
+    frames, labels = make_clip(34, 65, 97, K, 3)
+    first = labels[0].clone()
+    first[first == 2] = 0
+    np.random.seed(6)
+    run_sequence_device(model, frames, first, K, mem_every=2, unc_ratio=0.3)
+    np.random.seed(6)
+    _, probs = run_sequence(model, frames, labels[0], K, mem_every=2, device=torch.device("cuda:0"), keep_probs=True)
+    for p in probs:
+        assert p.shape[1] == K + 1
+        assert (p.sum(1) - 1.0).abs().max().item() < 1e-5
+        assert (p[:, 2] > 0).any()
+
+
+def test_new_sequence_same_shape_one_frame_bank(model):
+    """Two DIFFERENT clips of the same size and object count, each with a bank that never grows past the ground-truth
+    frame (mem_every = -1): the bank-dependent graph of the first sequence must not be replayed for the second (its
+    version key is never reused), so graph replay and plain launches agree bit for bit on both."""
+    from aocb200.sequence import run_sequence
+    from aocb200.synth import make_clip
+    K = 2
+    dev = torch.device("cuda:0")
+    eng = model.engine()
+    clips = [make_clip(s, 65, 97, K, 3) for s in (41, 42)]
+    outs = {}
+    for graphs in (True, False):
+        old, eng.use_graphs = eng.use_graphs, graphs
+        try:
+            for i, (frames, labels) in enumerate(clips):
+                np.random.seed(50 + i)
+                outs[(graphs, i)] = run_sequence(model, frames, labels[0], K, mem_every=-1, device=dev)
+        finally:
+            eng.use_graphs = old
+    for i in range(2):
+        for a, b in zip(outs[(True, i)], outs[(False, i)]):
+            assert torch.equal(a, b), "graph replay differs from plain launches on sequence %d" % i
+
+
+def test_object_count_changes_between_sequences(model):
+    """K is read from the gt_ids of THIS call (fresh tensors per sequence may recycle Python ids)."""
+    from aocb200.sequence import run_sequence
+    from aocb200.synth import make_clip
+    dev = torch.device("cuda:0")
+    for K in (3, 1, 2):
+        frames, labels = make_clip(60 + K, 65, 97, K, 3)
+        np.random.seed(K)
+        _, probs = run_sequence(model, frames, labels[0], K, mem_every=2, device=dev, keep_probs=True)
+        assert all(p.shape[1] == K + 1 for p in probs)

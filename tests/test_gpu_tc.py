@@ -135,15 +135,45 @@ def test_conv_tc_tf32_mode(eng):
     eng.tc_conv = True
     c = _conv_tc_case
     try:
-        assert eng.L.set_option(b"conv_f16", 0) == 0
-        eng._wpacked.clear()                                    # the packed weight image depends on the operand mode
+        eng.conv_mode = 0                                       # AOC_CONV_TF32X3: a per-call argument, recorded per weight image
         c(eng, 1, 31, 54, 256, 256, 3, 1, 1, 1, relu=True, seed=131)
         c(eng, 2, 25, 33, 128, 512, 1, 1, 0, 1, scale=True, shift=True, in_relu=True, bias=False, seed=132)
         c(eng, 1, 121, 213, 64, 64, 3, 1, 1, 1, relu=True, res=True, seed=133)
         c(eng, 1, 31, 54, 2048, 256, 3, 1, 12, 12, relu=True, seed=134)
     finally:
-        eng.L.set_option(b"conv_f16", 1)
-        eng._wpacked.clear()
+        eng.conv_mode = 1
+
+
+def test_conv_overflow_flag(eng):
+    """The split-fp16 operand mode clamps at 65504.  A convolution whose input reaches 1e5 must raise the sticky device
+    word (and give a wrong result); the same layer in 3xTF32 mode must not raise it and must be right."""
+    eng.tc_conv = True
+    g = torch.Generator().manual_seed(7)
+    N, H, W, Cin, Cout = 1, 20, 30, 64, 64
+    x = torch.randn(N, Cin, H, W, generator=g)
+    x[0, 5, 7, 11] = 1.0e5
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    want = F.conv2d(x.double(), w.double(), None, 1, 1, 1)
+    eng.w.conv["tc.ovf"] = (w.permute(0, 2, 3, 1).contiguous().cuda(), None, (Cout, 3, 3, Cin))
+    res = {}
+    try:
+        for mode in (1, 0):
+            eng.conv_mode = mode
+            eng._ovf.zero_()
+            out = eng.conv(to_T(x, eng), "tc.ovf", pad=1)
+            torch.cuda.synchronize()
+            res[mode] = (int(eng._ovf.item()), (from_T(out).double() - want).abs().max().item())
+    finally:
+        eng.conv_mode = 1
+        eng._ovf.zero_()
+    print("[parity] conv with a 1e5 activation: split-fp16 flag %d err %.3e | 3xTF32 flag %d err %.3e" % (res[1] + res[0]))
+    assert res[1][0] == 1 and res[1][1] > 1.0, res      # clamped at 65504: off by ~3.4e4 * |w|
+    assert res[0][0] == 0 and res[0][1] < 1e-2, res     # 1e5 * 1e-7 relative
+    # below the guard threshold nothing is raised
+    x[0, 5, 7, 11] = 3.0e4
+    out = eng.conv(to_T(x, eng), "tc.ovf", pad=1)
+    torch.cuda.synchronize()
+    assert int(eng._ovf.item()) == 0
 
 
 def test_conv_tc_chunking(eng):
