@@ -328,6 +328,83 @@ __global__ void __launch_bounds__(128) proxy_match_kernel(const float* __restric
     }
 }
 
+// The same matching for a proxy table of any width (kmax = 64: P [O][2*kmax+4][EMB]): the slots are walked in chunks of
+// 32 (centroid chunks, then centroid_avg chunks, then the mean proxy), per-proxy arithmetic identical to the kernel above.
+__global__ void __launch_bounds__(128) proxy_match_wide_kernel(const float* __restrict__ q, int HW,
+                                                                const float* __restrict__ P,
+                                                                const int* __restrict__ pvalid,
+                                                                const float* __restrict__ bias, int O, int kmax,
+                                                                float* __restrict__ out_cluster,
+                                                                float* __restrict__ out_proxy) {
+    extern __shared__ __align__(16) float smf[];
+    float* Qs = smf;                 // [EMB][128]
+    float* Ps = smf + EMB * 128;     // [EMB][32]
+    __shared__ float p2[32];
+    __shared__ int pv[32];
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * 128;
+    const int slots = 2 * kmax + 4;
+    for (int i = tid; i < 128 * EMB4; i += 128) {
+        int r = i / EMB4, c4 = i - r * EMB4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < HW) v = ldg4(q + (size_t)(q0 + r) * EMB + c4 * 4);
+        Qs[(c4 * 4 + 0) * 128 + r] = v.x; Qs[(c4 * 4 + 1) * 128 + r] = v.y;
+        Qs[(c4 * 4 + 2) * 128 + r] = v.z; Qs[(c4 * 4 + 3) * 128 + r] = v.w;
+    }
+    __syncthreads();
+    float q2 = 0.f;
+    for (int c = 0; c < EMB; ++c) { float v = Qs[c * 128 + tid]; q2 = fmaf(v, v, q2); }
+    for (int o = 0; o < O; ++o) {
+        float m0 = INFINITY, m1 = INFINITY, dp = 0.f;
+        for (int s0 = 0; s0 <= 2 * kmax; s0 += 32) {          // last chunk: the mean proxy alone
+            const int n = min(32, 2 * kmax + 1 - s0);
+            __syncthreads();
+            for (int i = tid; i < 32 * EMB; i += 128) {
+                int j = i / EMB, c = i - j * EMB;
+                Ps[c * 32 + j] = j < n ? __ldg(P + ((size_t)o * slots + s0 + j) * EMB + c) : 0.f;
+            }
+            if (tid < 32) pv[tid] = tid < n ? pvalid[o * slots + s0 + tid] : 0;
+            __syncthreads();
+            if (tid < 32) {
+                float s = 0.f;
+                for (int c = 0; c < EMB; ++c) { float v = Ps[c * 32 + tid]; s = fmaf(v, v, s); }
+                p2[tid] = s;
+            }
+            __syncthreads();
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int c = 0; c < EMB; ++c) {
+                float qv = Qs[c * 128 + tid];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 pp = *reinterpret_cast<const float4*>(Ps + c * 32 + j4 * 4);
+                    acc[j4 * 4 + 0] = fmaf(qv, pp.x, acc[j4 * 4 + 0]);
+                    acc[j4 * 4 + 1] = fmaf(qv, pp.y, acc[j4 * 4 + 1]);
+                    acc[j4 * 4 + 2] = fmaf(qv, pp.z, acc[j4 * 4 + 2]);
+                    acc[j4 * 4 + 3] = fmaf(qv, pp.w, acc[j4 * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float d = fmaf(-2.0f, acc[j], q2 + p2[j]);
+                if (s0 == 2 * kmax) { if (j == 0) dp = d; }
+                else if (s0 < kmax) { if (pv[j]) m0 = fminf(m0, d); }
+                else                { if (pv[j]) m1 = fminf(m1, d); }
+            }
+        }
+        if (m0 == INFINITY) m0 = AOC_WRONG_LABEL_PAD;
+        if (m1 == INFINITY) m1 = AOC_WRONG_LABEL_PAD;
+        if (q0 + tid < HW) {
+            float b = __ldg(bias + o);
+            size_t idx = (size_t)(q0 + tid) * O + o;
+            out_cluster[idx * 2 + 0] = sig2(m0 + b);
+            out_cluster[idx * 2 + 1] = sig2(m1 + b);
+            out_proxy[idx] = sig2(dp + b);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // head pooling: per-object sums of embeddings (+ total) over `total` flat pixels.
 // part: [nblk][MAXO+1][EMB] floats, pcnt: [nblk][MAXO] ints.
@@ -617,9 +694,19 @@ extern "C" int aoc_global_match_finalize_f32(const float* mins, const int* meta,
 }
 
 extern "C" int aoc_proxy_match_f32(const float* q, int HW, const float* P, const int* pvalid, const float* bias,
-                                   int O, float* out_cluster, float* out_proxy, cudaStream_t stream) {
+                                   int O, int kmax, float* out_cluster, float* out_proxy, cudaStream_t stream) {
     AOC_CHECK_ARG(q && P && pvalid && bias && out_cluster && out_proxy, "null pointer");
     AOC_CHECK_ARG(O >= 1 && O <= MAXO && HW > 0, "bad dims");
+    AOC_CHECK_ARG(kmax == 16 || kmax == AOC_KMEANS_MAX_K, "kmax must be 16 or 64");
+    if (kmax != 16) {
+        static PerDeviceOnce attr_w;
+        size_t smem_w = (size_t)(EMB * 128 + EMB * 32) * sizeof(float);
+        if (attr_w.first())
+            cudaFuncSetAttribute(proxy_match_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        proxy_match_wide_kernel<<<cdiv(HW, 128), 128, smem_w, stream>>>(q, HW, P, pvalid, bias, O, kmax, out_cluster,
+                                                                      out_proxy);
+        return launch_status("aoc_proxy_match_f32");
+    }
     static PerDeviceOnce attr_done;
     size_t smem = (size_t)(EMB * 128 + EMB * NPX) * sizeof(float);
     if (attr_done.first()) {

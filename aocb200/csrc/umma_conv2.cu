@@ -66,6 +66,7 @@ struct Conv2P {
     int tiles_n, total_tiles;
     int ksplit;             // split-K factor: work item = (tile, K slice); slices write raw partial sums to `ws`
     float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
+    int* ws_cnt;            // [total_tiles] arrival counters of the K slices (zero between launches)
     unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event < 16][stage < 256]
     int vec_out;
     int* overflow;          // optional device word: set to 1 when a split-fp16 activation operand reaches the fp16 range (|x| >= 6e4)
@@ -554,6 +555,50 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     }
                 }
             }
+            if (SK) {
+                // ---- split-K: the slice that arrives LAST at the tile's counter adds the ksplit partial tiles in slice
+                // order (deterministic whichever slice that is), applies bias / residual / ReLU and writes y -- the
+                // separate finish kernel (65 launches per frame on the 31x54 backbone maps) is gone.  The other slices'
+                // partial sums are read with ld.global.cg: they were written by other SMs during this launch.
+                int* flag = reinterpret_cast<int*>(smem + Cfg::STAT_OFF);
+                const int tile_id = t / p.ksplit;
+                __threadfence();
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (threadIdx.x == 256) {
+                    const int old = atomicAdd(p.ws_cnt + tile_id, 1);
+                    const int last = old == p.ksplit - 1;
+                    if (last) p.ws_cnt[tile_id] = 0;                 // every slice has arrived: ready for the next launch
+                    *flag = last;
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const bool last = *flag != 0;
+                asm volatile("bar.sync 2, 256;" ::: "memory");          // (the flag word is rewritten by the next item)
+                if (last) {
+                    __threadfence();
+                    const size_t Mtot = (size_t)p.N * p.Ho * p.Wo;
+                    const int i0 = threadIdx.x - 256;                    // 0..255 over 128 pixels x (TN / 4) float4 columns
+                    constexpr int C4 = TN / 4;
+                    for (int i = i0; i < C2_BM * C4; i += 256) {
+                        const int m = i / C4, c = (i - m * C4) * 4;
+                        const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
+                        const int co = tl.n0 + c;
+                        if (ho >= p.Ho || wo >= p.Wo || co >= p.Cout) continue;   // (Cout % 4 == 0 on this path)
+                        const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
+                        float4 a = __ldcg(reinterpret_cast<const float4*>(p.ws + pix * p.Cout + co));
+                        for (int k = 1; k < p.ksplit; ++k) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)k * Mtot + pix) * p.Cout + co));
+                            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                        }
+                        if (p.bias) { const float4 b = ldg4(p.bias + co); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+                        if (p.res) {
+                            const float4 r = ldg4(p.res + pix * p.ldres + co);
+                            a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                        }
+                        if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+                        *reinterpret_cast<float4*>(p.y + pix * p.ldy + co) = a;
+                    }
+                }
+            }
             if (!SK && p.tile_stats) {
                 // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -762,30 +807,6 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     }
 }
 
-// y[m][co] = sum_ks ws[ks][m][co] + bias (+ residual) (ReLU); slices added in index order (deterministic)
-__global__ void conv2_splitk_finish_kernel(const float* __restrict__ ws, int S, long long M, int Cout,
-                                           const float* __restrict__ bias, const float* __restrict__ res, int ldres,
-                                           float* __restrict__ y, int ldy, int relu) {
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int C4 = Cout >> 2;
-    const long long total = M * C4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4) * 4;
-        const long long m = i / C4;
-        float4 a = ldg4(ws + (size_t)m * Cout + c);
-        for (int k = 1; k < S; ++k) {
-            const float4 v = ldg4(ws + ((size_t)k * M + m) * Cout + c);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
-        if (bias) { const float4 b = ldg4(bias + c); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
-        if (res) { const float4 r = ldg4(res + (size_t)m * ldres + c); a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w; }
-        if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-        *reinterpret_cast<float4*>(y + (size_t)m * ldy + c) = a;
-    }
-}
-
 // w [Cout][taps][Cin] fp32 -> weight image: [row block of 128][stage it = (tap, cc)][ks][hi|lo][128 rows x 8 floats]
 __global__ void conv2_pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int ncc,
                                           int rows_padded, uint8_t* __restrict__ out) {
@@ -867,6 +888,7 @@ static EncodeTiledFn get_encode() {
 }
 
 constexpr int C2_MAX_KSPLIT = 8;
+constexpr size_t C2_WS_HEADER = 4096;   // split-K arrival counters (one int per output tile) in front of the partial sums
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
 int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels
 int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
@@ -888,14 +910,17 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     // stages) spread it.  Needs the caller's workspace for the partial sums; the epilogue fusions (statistics) do not apply.
     q.ksplit = 1;
     q.ws = nullptr;
+    q.ws_cnt = nullptr;
     const long long M = (long long)p.N * p.Ho * p.Wo;
     const int R = p.taps * ((p.ncc + 1) / 2);
     if (g_conv_splitk && q.total_tiles * 2 <= sms && !p.tile_stats && p.Cout % 4 == 0 && p.vec_out && workspace) {
         int S = sms / q.total_tiles;
         if (S > C2_MAX_KSPLIT) S = C2_MAX_KSPLIT;
         if (S > R / 4) S = R / 4;
-        while (S > 1 && (size_t)S * M * p.Cout * sizeof(float) > ws_bytes) --S;
-        if (S > 1) { q.ksplit = S; q.ws = (float*)workspace; }
+        const size_t hdr = C2_WS_HEADER;
+        if (ws_bytes < hdr || (size_t)q.total_tiles * sizeof(int) > hdr) S = 1;
+        while (S > 1 && hdr + (size_t)S * M * p.Cout * sizeof(float) > ws_bytes) --S;
+        if (S > 1) { q.ksplit = S; q.ws = (float*)((char*)workspace + hdr); q.ws_cnt = (int*)workspace; }
     }
     const int items = q.total_tiles * q.ksplit;
     const int grid = items < sms ? items : sms;                       // persistent: one CTA per SM walks the work list
@@ -907,12 +932,6 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
     if (q.ksplit > 1) {
         cudaLaunchKernelEx(&cfg, conv2_kernel<TN, true, F16>, map, q);
-        const long long total4 = M * (p.Cout / 4);
-        int blocks = (int)((total4 + 255) / 256);
-        if (blocks > sms * 8) blocks = sms * 8;
-        cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
-        cudaLaunchKernelEx(&cfg, conv2_splitk_finish_kernel, (const float*)q.ws, q.ksplit, M, p.Cout, p.bias, p.res,
-                           p.ldres, p.y, p.ldy, p.relu);
     } else {
         cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false, F16>, map, q);
     }
@@ -971,7 +990,7 @@ extern "C" size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
     if (Ho <= 0 || Wo <= 0) return 0;
-    return (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
+    return C2_WS_HEADER + (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
 }
 
 extern "C" int aoc_conv_trace(void* device_buffer_16x256_u64) {

@@ -14,7 +14,8 @@ from .lib import lib
 from .params import EMB, HEAD
 
 MAXO = 16
-PROXY_SLOTS = 36
+PROXY_SLOTS = 36        # proxy slots per object at cluster_num <= 16 (2 * kmax + 4; see Engine.kmax)
+KMEANS_MAX_K = 64
 META_INTS = 2 * MAXO + 3
 BANK_ALIGN = 256
 
@@ -169,7 +170,7 @@ class Engine:
         self.w = Weights(state_dict, self.dev)
         self.bank = Bank()
         self.kmeans_iters = 20
-        self.cluster_num = 16
+        self.cluster_num = 16           # matching.py:507; up to KMEANS_MAX_K (the kernels run at width 16 or 64)
         self.debug = {}
         self.keep_debug = False
         self.force_proxies = None       # test hook, see _apply_forced_proxies
@@ -212,6 +213,16 @@ class Engine:
 
     # ------------------------------------------------------------------ plumbing
     @property
+    def kmax(self):
+        """compile-time width of the k-means / proxy kernels for the current cluster_num"""
+        assert 1 <= self.cluster_num <= KMEANS_MAX_K, "cluster_num must be in 1..%d" % KMEANS_MAX_K
+        return 16 if self.cluster_num <= 16 else KMEANS_MAX_K
+
+    @property
+    def proxy_slots(self):
+        return 2 * self.kmax + 4
+
+    @property
     def stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
@@ -233,13 +244,16 @@ class Engine:
     def new(self, N, H, W, C):
         return T(self.empty(N * H * W * C), N, H, W, C)
 
-    def ws(self, name, nbytes):
-        """persistent scratch (never handed to the caller)"""
+    def ws(self, name, nbytes, zero_head=0):
+        """persistent scratch (never handed to the caller); zero_head: bytes at the front that the library expects zeroed
+        when it first sees the buffer (split-K arrival counters) -- cleared once, at allocation"""
         b = self._ws.get(name)
         if b is None or b.numel() < nbytes:
             if b is not None:
                 self._ws_keep.append(b)      # a captured graph may still point at the superseded buffer
             b = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+            if zero_head:
+                self.L.fill_u32(b.data_ptr(), 0, zero_head // 4, self.stream)
             self._ws[name] = b
         return b
 
@@ -271,7 +285,7 @@ class Engine:
             wsp, wsn = None, 0
             if x.N * Ho * Wo <= 128 * 74 and not stats:       # few pixel tiles: let the library split K
                 wsn = self.L.conv_workspace_bytes(x.N, x.H, x.W, Cout, kh, kw, stride, pad, dil)
-                wsp = self.ws("conv_splitk", wsn).data_ptr()
+                wsp = self.ws("conv_splitk", wsn, zero_head=4096).data_ptr()
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
                                   _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
                                   out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,
@@ -524,7 +538,7 @@ class Engine:
         """k chain + init rows from numpy's GLOBAL RNG, exactly the stream scipy's kmeans2(minit='points') consumes
         (matching.py:556,562): one np.random.choice per object with pixels, in id order."""
         kk = np.zeros(MAXO, dtype=np.int32)
-        init = np.zeros((MAXO, 16), dtype=np.int32)
+        init = np.zeros((MAXO, self.kmax), dtype=np.int32)
         k = self.cluster_num
         counts = ix["counts"]
         for o in range(O):
@@ -554,21 +568,22 @@ class Engine:
             L.global_match_simt_f32(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), bias.data_ptr(), O,
                                     mins.data_ptr(), g.data_ptr(), st)
         # --- adaptive object proxies (matching.py:533-595)
-        cent = self.empty(MAXO * 16 * EMB)
+        kmax, slots = self.kmax, self.proxy_slots
+        cent = self.empty(MAXO * kmax * EMB)
         labels = self.empty(max(rows, 1), torch.int32)
-        P = self.zeros(MAXO * PROXY_SLOTS * EMB)
-        pvalid = self.zeros(MAXO * PROXY_SLOTS, torch.int32)
-        kws = L.kmeans_workspace_bytes(ix["maxrows"], O)
+        P = self.zeros(MAXO * slots * EMB)
+        pvalid = self.zeros(MAXO * slots, torch.int32)
+        kws = L.kmeans_workspace_bytes(ix["maxrows"], O, kmax)
         L.kmeans_proxies_f32(S.data_ptr(), meta.data_ptr(), ix["nat2sorted"].data_ptr(), kk_d.data_ptr(),
-                             init_d.data_ptr(), O, ix["maxrows"], self.kmeans_iters, cent.data_ptr(), labels.data_ptr(),
-                             P.data_ptr(), pvalid.data_ptr(), self.ws("kmeans", kws).data_ptr(), kws, st)
+                             init_d.data_ptr(), O, ix["maxrows"], self.kmeans_iters, kmax, cent.data_ptr(),
+                             labels.data_ptr(), P.data_ptr(), pvalid.data_ptr(), self.ws("kmeans", kws).data_ptr(), kws, st)
         if self.force_proxies is not None:
             self._apply_forced_proxies(P, pvalid, O)
         # --- bank attention heads / k=1 proxies (attention.py:155-189)
         hws = L.head_pool_workspace_bytes(max(total, hw))
         hbuf = self.ws("headpool", hws)
         L.head_pool_f32(bk.emb_all.data_ptr(), bk.ids_all.data_ptr(), total, O, 1e-5, head.data_ptr(), HEAD, 0, EMB,
-                        P.data_ptr() + 4 * 32 * EMB, PROXY_SLOTS * EMB, hbuf.data_ptr(), hws, st)
+                        P.data_ptr() + 4 * 2 * kmax * EMB, slots * EMB, hbuf.data_ptr(), hws, st)
         return g, P, pvalid, cent, labels
 
     def _apply_forced_proxies(self, P, pvalid, O):
@@ -579,6 +594,7 @@ class Engine:
         compared bit for bit on identical inputs in tests/test_gpu_ops.py.  Plain launches only."""
         assert not torch.cuda.is_current_stream_capturing(), "force_proxies needs AOCB200_GRAPHS=0 / use_graphs = False"
         f = self.force_proxies
+        assert self.kmax == 16
         Pv, vv = P.view(MAXO, PROXY_SLOTS, EMB), pvalid.view(MAXO, PROXY_SLOTS)
         ar = torch.arange(16, device=self.dev).view(1, 16)
         for key, cnt, lo in (("prox_cen", "prox_ncen", 0), ("prox_avg", "prox_navg", 16)):
@@ -600,7 +616,8 @@ class Engine:
         # --- cluster-level + proxy-level matching (matching.py:602-637, :149-197)
         gc = self.empty(hw * O * 2)
         gp = self.empty(hw * O)
-        L.proxy_match_f32(q.ptr, hw, P.data_ptr(), pvalid.data_ptr(), bias.data_ptr(), O, gc.data_ptr(), gp.data_ptr(), st)
+        L.proxy_match_f32(q.ptr, hw, P.data_ptr(), pvalid.data_ptr(), bias.data_ptr(), O, self.kmax, gc.data_ptr(),
+                          gp.data_ptr(), st)
         # --- local matching on the half-resolution grid (matching.py:2710-2851)
         hh, ww = h // 2 + 1, w // 2 + 1
         ldl = (6 * O + 3) // 4 * 4
@@ -881,6 +898,7 @@ class Engine:
         self.conv_mode = 0
         self.L.fill_u32(self._ovf.data_ptr(), 0, 1, self.stream)
         self._segA.clear(); self._static.clear()            # graphs captured with split-fp16 kernels / weight images
+        self._cap_stream = self._pool = None                # (their memory pool dies with its last graph: take a new one)
         for slot in self._ovf_ring:
             slot[2][0] = None
         msg = ("aocb200: a convolution input of frame %d reached the fp16 range (|x| >= 6e4); the split-fp16 operand "
@@ -1015,15 +1033,15 @@ class Engine:
         memory = list(memory_prev_list[0])
 
         # ---- static inputs of this (size, object count)
-        keyS = (h, w, O)
+        keyS = (h, w, O, self.kmax)
         st = self._static.get(keyS)
         if st is None:
             st = dict(prev_e=self.empty(hw * EMB), prev_ids=self.empty(hw, torch.uint8), head=self.empty(O * HEAD),
-                      kk=self.empty(MAXO, torch.int32), init=self.empty(MAXO * 16, torch.int32),
-                      g=self.empty(hw * O), P=self.empty(MAXO * PROXY_SLOTS * EMB),
-                      pvalid=self.empty(MAXO * PROXY_SLOTS, torch.int32),
+                      kk=self.empty(MAXO, torch.int32), init=self.empty(MAXO * self.kmax, torch.int32),
+                      g=self.empty(hw * O), P=self.empty(MAXO * self.proxy_slots * EMB),
+                      pvalid=self.empty(MAXO * self.proxy_slots, torch.int32),
                       mem=[self.new(O, (h + 1) // 2, (w + 1) // 2, 256), self.new(O, (h + 1) // 2, (w + 1) // 2, 256)],
-                      host=[(torch.empty(MAXO * 17, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                      host=[(torch.empty(MAXO * (1 + self.kmax), dtype=torch.int32).pin_memory(), torch.cuda.Event())
                             for _ in range(4)], turn=0, segF=None, segC={})
             self._static[keyS] = st
         # ---- bank index (host sync only when the bank changed) and this frame's RNG draws
@@ -1069,7 +1087,7 @@ class Engine:
                     front()                                  # first use: warm-up (workspaces)
                 else:                                        # workspaces must not be (re)allocated inside a capture
                     self.ws("gm_tc", self.L.global_match_tc_workspace_bytes(hw, ix["rows"]))
-                    self.ws("kmeans", self.L.kmeans_workspace_bytes(ix["maxrows"], O))
+                    self.ws("kmeans", self.L.kmeans_workspace_bytes(ix["maxrows"], O, self.kmax))
                     self.ws("headpool", self.L.head_pool_workspace_bytes(max(ix["total"], hw)))
                 gF, _ = self._capture(front)
                 segF = dict(graph=gF, version=ix["version"], emb=emb)

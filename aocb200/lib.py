@@ -48,7 +48,7 @@ class AocError(RuntimeError):
 
 
 # CUDA kernels launched by one call of each entry point (everything else launches exactly one); used for the
-# `gpu_launches` figure of bench.py.  aoc_kmeans_proxies_f32 launches 1 + 2*iters + 2 (counted by the caller).
+# `gpu_launches` figure of bench.py.
 KERNELS_PER_CALL = {
     "aoc_channel_stats_f32": 2, "aoc_affine_stats_nc_f32": 2, "aoc_bank_index_build": 4, "aoc_global_match_simt_f32": 2, "aoc_global_match_tc": 10,
     "aoc_head_pool_f32": 2, "aoc_dyn_logits_f32": 2, "aoc_gemm_tf32x3_test": 3,
@@ -93,10 +93,7 @@ class _Lib:
                 raise AocError("%s failed (%d): %s" % (name, rc, self.cdll.aoc_last_error_string().decode()))
             if not is_query:
                 self.calls += 1
-                if name == "aoc_kmeans_proxies_f32":
-                    self.launches += 3 + 2 * a[7]
-                else:
-                    self.launches += per_call
+                self.launches += per_call
             return rc
         return call
 

@@ -222,7 +222,7 @@ def kernel_profile(model, frames, first, device, n_frames):
         iters = km[0][2][names.index("iters")]
         # algorithmic bytes of the adaptive-proxy step = iters * (bank rows with an object) * 100 floats
         out["kmeans"] = {"launches": len(km), "ms": ms, "bytes": float(iters) * sum(km_rows) * 400.0,
-                         "kernels_per_call": 3 + 2 * iters}
+                         "kernels_per_call": 1}
 
     def arg(name, fn, a):
         return a[[n for _, n in L.protos[fn][1]].index(name)]
@@ -366,9 +366,11 @@ def main():
                               "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
                               "note": note}
         for key, nm, note in (
-                ("kmeans", "kmeans_step/reduce (adaptive object proxies: Lloyd assignment + centroid reduction, no tensor cores)",
-                 "algorithmic bytes = iters x bank rows x 400 B; the rows of a 480p bank fit the 126 MB L2, so a fraction "
-                 "above 1 would be L2-resident traffic, not HBM"),
+                ("kmeans", "kmeans_persistent_kernel (adaptive object proxies: all Lloyd rounds -- assignment + centroid reduction -- in one cooperative launch, no tensor cores)",
+                 "algorithmic bytes = iters x bank rows x 400 B (SURVEY 8d); the rows are read from L2/HBM once per call "
+                 "when the bank's row tiles fit the SMs' shared memory (<= 3 frames at 480p) and once per round otherwise, "
+                 "and a 480p bank fits the 126 MB L2 -- so this is shared-memory / L2-resident traffic measured against "
+                 "the HBM copy peak, and a fraction above 1 would be legitimate"),
                 ("affine_stats", "affine_stats_partial (GroupNorm apply + residual + ReLU + next block's statistics)",
                  "algorithmic bytes = read x (+ residual) + write y"),
                 ("film_stats", "cond_phi / channel_stats_partial (FiLM conditioning: phi map pass, masked pooling pass; GCT statistics)",

@@ -39,8 +39,8 @@ typedef struct CUstream_st* cudaStream_t;
 #define AOC_EARCH (-3)    /* device is not sm_100 */
 
 #define AOC_MAX_OBJECTS 16   /* O = K+1 slots */
-#define AOC_KMEANS_MAX_K 16  /* cluster_num, matching.py:507 */
-#define AOC_PROXY_SLOTS 36   /* per object: 16 centroids, 16 centroid_avg, 1 mean proxy, 3 pad */
+#define AOC_KMEANS_MAX_K 64  /* largest cluster_num (matching.py:507; the reference wires 16) */
+#define AOC_PROXY_SLOTS 36   /* per object at kmax = 16: 16 centroids, 16 centroid_avg, 1 mean proxy, 3 pad (2*kmax + 4) */
 #define AOC_META_INTS (2 * AOC_MAX_OBJECTS + 3)
 
 int aoc_version(void);
@@ -87,7 +87,9 @@ int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, 
                        int dil, int relu, int chunk_stages, int operand_mode, int* overflow_flag, void* workspace,
                        size_t ws_bytes, cudaStream_t stream);
 /* workspace (optional, aoc_conv_workspace_bytes): partial sums for split-K, used when the layer has too few output
- * tiles to fill the chip (the 31x54 maps of the backbone); without it such layers run unsplit. */
+ * tiles to fill the chip (the 31x54 maps of the backbone); without it such layers run unsplit.  Its first 4096 bytes
+ * are arrival counters that must be ZERO when the caller first hands the buffer over; every launch leaves them zero
+ * again (the K slice that arrives last at a tile adds the slices in index order, finishes the tile and resets it). */
 size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
 /* tile_stats (optional): [N * aoc_conv_tiles_per_image(...)][2][Cout] floats receiving, per 128-pixel output tile, the
  * per-channel sum and sum of squares of the stored output -- the GroupNorm / GCT statistics of the next layer come
@@ -192,8 +194,9 @@ int aoc_global_match_tc(const float* q, int HW, const float* S, const float* r2,
                         const float* bias, int O, void* workspace, size_t ws_bytes, float* out, cudaStream_t stream);
 int aoc_global_match_finalize_f32(const float* mins, const int* meta, const float* bias, int HW, int O, float* out,
                                   cudaStream_t stream);
-/* cluster level (matching.py:602-637) and k=1 proxy level (matching.py:149-197): out_cluster [HW][O][2], out_proxy [HW][O] */
-int aoc_proxy_match_f32(const float* q, int HW, const float* P, const int* pvalid, const float* bias, int O,
+/* cluster level (matching.py:602-637) and k=1 proxy level (matching.py:149-197): out_cluster [HW][O][2], out_proxy [HW][O];
+ * P / pvalid / kmax as produced by aoc_kmeans_proxies_f32 */
+int aoc_proxy_match_f32(const float* q, int HW, const float* P, const int* pvalid, const float* bias, int O, int kmax,
                         float* out_cluster, float* out_proxy, cudaStream_t stream);
 size_t aoc_head_pool_workspace_bytes(int total_pixels);
 /* calculate_attention_head_for_eval_p_m (attention.py:155-189): masked means written into head rows */
@@ -210,11 +213,17 @@ int aoc_prehead_assemble_f32(const float* g, const float* gc, const float* gp, c
 int aoc_broadcast_rows_f32(const float* x, float* y, int N, int HW, int C, int ldx, int ldy, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- adaptive object proxies (kmeans.cu) */
-size_t aoc_kmeans_workspace_bytes(int max_rows_per_object, int O);
-/* scipy.cluster.vq.kmeans2(X_i, k, 'points', iter) per object + centroid_avg (matching.py:533-595) */
+size_t aoc_kmeans_workspace_bytes(int max_rows_per_object, int O, int kmax);
+/* scipy.cluster.vq.kmeans2(X_i, k, 'points', iter) per object + centroid_avg (matching.py:533-595, cluster_num :507) in
+ * ONE persistent cooperative launch (grid-wide barriers between assignment and update; row tiles resident in shared
+ * memory when the bank fits the chip).  kmax = 16 (the reference's cluster_num) or AOC_KMEANS_MAX_K = 64 is the
+ * compile-time width the call runs at; kk[o] <= kmax clusters for object o (0 = none), init_idx [O][kmax] object-local
+ * rows drawn by the host RNG.  Outputs: cent [O][kmax][100], labels (int32 per sorted bank row),
+ * P [O][2*kmax+4][100] (slots 0..kmax-1 centroids, kmax..2*kmax-1 centroid_avg, 2*kmax the mean proxy written by
+ * aoc_head_pool_f32) and pvalid [O][2*kmax+4]. */
 int aoc_kmeans_proxies_f32(const float* S, const int* meta, const int* nat2sorted, const int* kk, const int* init_idx,
-                           int O, int max_rows_per_object, int iters, float* cent, int* labels, float* P, int* pvalid,
-                           void* workspace, size_t ws_bytes, cudaStream_t stream);
+                           int O, int max_rows_per_object, int iters, int kmax, float* cent, int* labels, float* P,
+                           int* pvalid, void* workspace, size_t ws_bytes, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- output head (head.cu) */
 int aoc_dyn_logits_f32(const float* x, const float* wfg, const float* wbg, float* fg, float* bg, float* logits, int O,

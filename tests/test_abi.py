@@ -37,7 +37,7 @@ def test_version_and_error_string(built_lib):
 def test_workspace_queries(built_lib):
     assert built_lib.channel_stats_workspace_bytes(6, 25773, 256) == 6 * 101 * 2 * 256 * 8
     assert built_lib.bank_workspace_bytes(25773, 6) > 0
-    assert built_lib.kmeans_workspace_bytes(25773, 6) > 0
+    assert built_lib.kmeans_workspace_bytes(25773, 6, 16) > 0
     assert built_lib.head_pool_workspace_bytes(25773) > 0
 
 
