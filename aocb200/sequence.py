@@ -73,6 +73,113 @@ def run_sequence(model, frames, first_label, num_objects, mem_every=5, unc_ratio
     return (preds, probs_out) if keep_probs else preds
 
 
+def flip_w(t):
+    """utils/image.py:52-55 on the last (width) axis"""
+    return torch.flip(t, dims=[t.dim() - 1])
+
+
+def run_sequence_tta(model, samples, num_objects, mem_every=5, unc_ratio=1.0, device=None, on_frame=None):
+    """The reference eval loop WITH test-time augmentation (TEST_FLIP / TEST_MULTISCALE; eval_manager_mm.py:195-361):
+    every frame arrives as a list of augmented samples -- what MultiRestrictSize + MultiToTensor produce
+    (custom_transforms.py:387-487): per scale the plain and, with flipping, the mirrored image -- each augmentation keeps
+    its own memory bank / previous frame / decoder memory, the probabilities (all at the ORIGINAL size, mirrored ones
+    flipped back, :304) are averaged, and the averaged label map feeds every stream's bank and previous mask.
+
+    samples[t] = list over augmentations of dict(img [1,3,h_a,w_a], label [h_a,w_a] ints or None, flip bool); the
+    original size is samples[t][i]['size'] = (H, W) (default: the image size of augmentation 0).
+    Returns the list of label maps [H,W] for frames 1..T-1.
+
+    The loop is restated with its three order-dependent behaviours, because a drop-in has to hand the model exactly what
+    the reference hands it (pinned by tests/golden/eval_loop_tta_trace.pt, recorded from the reference's own loop):
+      1. the seen-label list is updated BETWEEN the augmentations of a ground-truth frame (:262-265 sits inside the
+         augmentation loop, after the filter of that augmentation);
+      2. the entropy map that decides label 125 is the LAST augmentation's -- computed from its probabilities before they
+         are flipped back, so in mirrored coordinates when that augmentation is mirrored (:266-270, :304, :339);
+      3. on a memory frame EVERY stream's confident bank mask is the unflipped map (:356-361), while a mirrored stream's
+         previous mask (and, on a ground-truth frame, its bank mask) is the flipped one (:343-345, :351-354).
+    A ground-truth label on a non-mirrored augmentation of a different size than the original cannot be joined by the
+    reference either (:322-325 mixes the sizes); that case raises here."""
+    dev = device
+    A = len(samples[0])
+    gt_ids = torch.tensor([num_objects], device=dev) if dev is not None else torch.tensor([num_objects])
+    ref_emb = [[] for _ in range(A)]
+    ref_conf = [[] for _ in range(A)]
+    prev_emb, prev_mask = [None] * A, [None] * A
+    memory = [[[None, None]] for _ in range(A)]
+    seen = []                                                                  # label_all_list
+    preds = []
+    for t, augs in enumerate(samples):
+        assert len(augs) == A
+        H, W = augs[0].get("size", tuple(augs[0]["img"].shape[-2:]))
+        all_preds, join, update = [], None, False
+        exist_probs = unc = None
+        for a, smp in enumerate(augs):
+            img = smp["img"] if dev is None else smp["img"].to(dev, non_blocking=True)
+            lab = smp.get("label")
+            if lab is not None:
+                lab = lab if dev is None else lab.to(dev)
+                lab4 = lab.view(1, 1, lab.shape[-2], lab.shape[-1])
+            probs, emb, memory[a] = model.forward_for_eval(memory[a], ref_emb[a], ref_conf[a], prev_emb[a], prev_mask[a],
+                                                           img, pred_size=[H, W], gt_ids=gt_ids)            # :246-249
+            if probs is not None:                                                                        # :252-261
+                keep = torch.zeros(probs.shape[1], device=probs.device)
+                ex = [i for i in range(probs.shape[1]) if i in seen]
+                keep[ex] = 1.0
+                exist_probs = probs[:, ex]
+                probs = probs * keep.view(1, -1, 1, 1)
+            if lab is not None:                                                                          # :262-265
+                for v in torch.unique(lab).tolist():
+                    if int(v) not in seen:
+                        seen.append(int(v))
+            if t == 0:                                                                                   # :267-277
+                assert lab is not None, "the first frame carries the ground-truth label"
+                ref_emb[a].append(emb); ref_conf[a].append(lab4)
+                prev_emb[a], prev_mask[a] = emb, lab4
+                continue
+            if smp["flip"]:
+                probs = flip_w(probs)                                                                    # :279-280
+            if not smp["flip"] and lab is not None and join is None:                                     # :283-284
+                join = lab
+            all_preds.append(probs)
+            if lab is not None:
+                ref_emb[a].append(emb)                                                                   # :290-291
+            else:
+                unc = shannon_entropy(exist_probs)                                                       # :300 (this augmentation's)
+                if mem_every > -1 and t % mem_every == 0:                                                # :303-306
+                    ref_emb[a].append(emb)
+                    update = True
+            prev_emb[a] = emb
+        if t == 0:
+            continue
+        mean = torch.mean(torch.cat(all_preds, dim=0), dim=0)                                            # :312-314
+        pred = torch.argmax(mean, dim=0)
+        if join is not None:                                                                             # :315-319
+            if tuple(join.shape[-2:]) != (H, W):
+                raise ValueError("a ground-truth label at an augmented size cannot be joined (eval_manager_mm.py:322-325)")
+            join = join.to(pred.device).long().view(H, W)
+            keepj = (join == 0).long()
+            pred = pred * keepj + join * (1 - keepj)
+        cur = pred.view(1, 1, H, W)
+        flipped = flip_w(pred).view(1, 1, H, W) if augs[-1]["flip"] else None                            # :321-323 (LAST augmentation)
+        for a, smp in enumerate(augs):
+            if join is not None:                                                                         # :326-343
+                if smp["flip"]:
+                    ref_conf[a].append(flipped)
+                else:
+                    u = shannon_entropy(exist_probs)[0, 0] * keepj
+                    unc = u.view(1, 1, H, W)
+                    region = (u > unc_ratio).long()
+                    ref_conf[a].append((pred * (1 - region) + 125 * region).view(1, 1, H, W))
+            prev_mask[a] = flipped if smp["flip"] else cur                                               # :345-348
+            if update:                                                                                   # :350-355
+                region = (unc.view(H, W) > unc_ratio).long()
+                ref_conf[a].append((pred * (1 - region) + 125 * region).view(1, 1, H, W))
+        preds.append(pred)
+        if on_frame is not None:
+            on_frame(t, mean, pred)
+    return preds
+
+
 class DeviceSequence:
     """The same bookkeeping with every piece of per-sequence state resident on the GPU: label maps
     are uint8 device tensors, the label-existence filter (eval_manager_mm.py:252-270), the argmax (:318-320) and the

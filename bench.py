@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AOC-Net per-frame inference path (BASELINE.json: 480p 5-object VOS frames/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one predicted frame of a synthetic YouTube-VOS-shaped 480p clip with 5 objects (BASELINE.json configs[2];
@@ -13,6 +13,11 @@ value  : frames/s with the clip's frames already resident in HBM (CUDA events, m
 e2e    : same, but every step copies its frame from pinned host memory (H2D) and reads the predicted label map
          back (D2H) inside the timed region.
 roofline / cpu_baseline: see DESIGN.md ("Measurement").
+parity : the other half of BASELINE.json's metric ("mask IoU vs ref"), measured on the frames the CPU baseline computes
+         anyway: the engine is fed the oracle's label maps and numpy seeds for those frames; argmax-equal pixel fraction,
+         IoU with utils/metric.py:3-34 semantics (engine mask vs oracle mask), max |dlogit|.
+--config: cfg3 (default) is the configuration the metric is quoted on; cfg2 / cfg4 / cfg5 are BASELINE.json's other
+         GPU configurations (their lines are kept under profiles/).
 """
 import argparse
 import json
@@ -27,9 +32,23 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+METRIC = "480p 5-object VOS frames/sec"        # BASELINE.json; --config cfg2/cfg4/cfg5 lines carry their workload in `config`
 
-H480, W480, K_OBJ = 480, 854, 5          # source resolution; MultiRestrictSize -> 481 x 849
 MEM_EVERY = 5
+# BASELINE.json configs[1..4].  480p sources go through MultiRestrictSize (-> 481 x 849); the 720p
+# and 1080p configurations run at native size (721 x 1281 -> features 181 x 321; 1073 x 1921 -> 269 x 481).
+CONFIGS = {
+    "cfg2": dict(src=(480, 854), K=3, restrict=1040, steps=29, cpu_frames=2,
+                 name="synthetic DAVIS-17-shaped 480p clip (480x854 -> %dx%d), 3 objects, 30 frames"),
+    "cfg3": dict(src=(480, 854), K=5, restrict=1040, steps=26, cpu_frames=2,
+                 name="synthetic YouTube-VOS-shaped 480p clip (480x854 -> %dx%d), 5 objects"),
+    "cfg4": dict(src=(720, 1280), K=10, restrict=10 ** 9, steps=12, cpu_frames=1,
+                 name="synthetic 720p clip (native %dx%d, features 181x321), 10 objects (k-means stress)"),
+    "cfg5": dict(src=(1080, 1920), K=5, restrict=10 ** 9, steps=99, cpu_frames=0,
+                 name="synthetic 1080p clip (native %dx%d, features 269x481), 5 objects, 100-frame sequence, bank growing to 20 frames"),
+}
+CFG = dict(CONFIGS["cfg3"])
+K_OBJ = CFG["K"]
 
 
 def peaks():
@@ -90,9 +109,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def workload_size():
+    from aocb200.synth import restrict_size
+    return restrict_size(CFG["src"][0], CFG["src"][1], CFG["restrict"])
+
+
 def make_workload(seed, n_frames):
-    from aocb200.synth import make_clip, restrict_size
-    H, W = restrict_size(H480, W480)
+    from aocb200.synth import make_clip
+    H, W = workload_size()
     frames, labels = make_clip(seed, H, W, K_OBJ, n_frames)
     return frames, labels[0], (H, W)
 
@@ -245,43 +269,92 @@ def kernel_profile(model, frames, first, device, n_frames):
     return out
 
 
-def cpu_baseline(frames, first, n_timed):
-    """The reference algorithm (oracle port, fp32 torch-on-CPU + scipy) on the host cores: predicted frames/s."""
+def pytorch_iou(pred, target, K, epsilon=1e-6):
+    """utils/metric.py:3-34 for one frame: mean over the K object ids of (|P & T| + eps) / (|P | T| + eps)"""
+    if K == 0:
+        return 1.0
+    ids = torch.arange(1, K + 1, device=pred.device).view(-1, 1, 1)
+    p, t = (pred.unsqueeze(0) == ids).float(), (target.unsqueeze(0) == ids).float()
+    inter = (p * t).sum((1, 2))
+    union = ((p + t) > 0).float().sum((1, 2))
+    return float(((inter + epsilon) / (union + epsilon)).mean())
+
+
+def cpu_baseline(frames, first, n_timed, model=None, device=None):
+    """The reference algorithm (oracle port, fp32 torch-on-CPU + scipy) on the host cores: predicted frames/s.
+    With `model`: the engine runs the same frames with the oracle's label maps and numpy seeds (outside the timed
+    sections) -> parity dict (argmax_equal, iou, max_abs_dlogit; worst frame of the sample)."""
     from aocb200.params import synthetic_state_dict
     from oracle.aoc_oracle import AOCOracle
     torch.set_num_threads(os.cpu_count())
     orc = AOCOracle(synthetic_state_dict(1234))
     H, W = frames.shape[2:]
     gt = torch.tensor([K_OBJ])
-    np.random.seed(1000)
+    par = None
+    dt = 0.0
     with torch.no_grad():
         _, emb, mem = orc.forward_for_eval([[None, None]], [], [], None, None, frames[0:1], [H, W], gt)
         lab = first.view(1, 1, H, W)
         ref_e, ref_m, prev_e, prev_m = [emb], [lab], emb, lab
-        t0 = time.perf_counter()
+        if model is not None:
+            _, g_emb, g_mem = model.forward_for_eval([[None, None]], [], [], None, None, frames[0:1].to(device), [H, W],
+                                                     K_OBJ)
+            g_ref_e, g_ref_m, g_prev_e, g_prev_m = [g_emb], [lab.to(device)], g_emb, lab.to(device)
+            par = {"argmax_equal": 1.0, "iou": 1.0, "max_abs_dlogit": 0.0, "frames": n_timed,
+                   "note": "engine vs the CPU oracle on the cpu_baseline frames, both fed the oracle's label maps and numpy "
+                           "seeds; worst frame; iou = utils/metric.py:3-34 of the engine's mask against the oracle's"}
         for t in range(1, n_timed + 1):
+            np.random.seed(5000 + t)
+            t0 = time.perf_counter()
             probs, emb, mem = orc.forward_for_eval(mem, ref_e, ref_m, prev_e, prev_m, frames[t:t + 1], [H, W], gt)
-            prev_e, prev_m = emb, torch.argmax(probs[0], 0).view(1, 1, H, W)
-        dt = time.perf_counter() - t0
-    return n_timed / dt, dt
+            pred = torch.argmax(probs[0], 0)
+            dt += time.perf_counter() - t0
+            if model is not None:
+                np.random.seed(5000 + t)
+                g_probs, g_emb, g_mem = model.forward_for_eval(g_mem, g_ref_e, g_ref_m, g_prev_e, g_prev_m,
+                                                               frames[t:t + 1].to(device), [H, W], K_OBJ)
+                g_pred = torch.argmax(g_probs[0], 0).cpu()
+                dl = (model.engine().last_logits.cpu() - orc.last_logits).abs().max().item()
+                par["argmax_equal"] = min(par["argmax_equal"], float((g_pred == pred).float().mean()))
+                par["iou"] = min(par["iou"], pytorch_iou(g_pred, pred, K_OBJ))
+                par["max_abs_dlogit"] = max(par["max_abs_dlogit"], dl)
+                m = pred.view(1, 1, H, W).to(device)
+                g_prev_e, g_prev_m = g_emb, m
+                if t % MEM_EVERY == 0:
+                    g_ref_e.append(g_emb); g_ref_m.append(m)
+            prev_e, prev_m = emb, pred.view(1, 1, H, W)
+            if t % MEM_EVERY == 0:
+                ref_e.append(emb); ref_m.append(prev_m)
+    return n_timed / dt, dt, par
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=26)
+    ap.add_argument("--steps", type=int, default=None, help="timed predicted frames (default: 26 for cfg3; per config otherwise)")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-frames", type=int, default=2, help="predicted frames timed for cpu_baseline")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="predicted frames timed for cpu_baseline (per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global CFG, K_OBJ
+    CFG = dict(CONFIGS[args.config])
+    K_OBJ = CFG["K"]
+    global METRIC
+    if args.config != "cfg3":
+        METRIC = "VOS frames/sec (%s)" % args.config
+    if args.steps is None:
+        args.steps = CFG["steps"]
+    if args.cpu_frames is None:
+        args.cpu_frames = CFG["cpu_frames"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    H, W = 481, 849
-    config = {"workload": "synthetic YouTube-VOS-shaped 480p clip (480x854 -> %dx%d), %d objects, 1 GT frame + %d warm-up + "
-                          "%d timed predicted frames, memory bank +1 frame every %d, one independent clip per GPU"
-                          % (H, W, K_OBJ, args.warmup, args.steps, MEM_EVERY),
+    H, W = workload_size()
+    config = {"workload": (CFG["name"] % (H, W)) + ", 1 GT frame + %d warm-up + %d timed predicted frames, memory bank +1 "
+                          "frame every %d, one independent clip per GPU" % (args.warmup, args.steps, MEM_EVERY),
+              "config": args.config,
               "l2": "no flush: per-step working set (>300 MB of activations + bank) exceeds the 126 MB L2",
               "precision": "fp32 I/O; fp32-faithful tensor-core kernels: convolution and matching contract split-fp16 operand pairs "
                            "(22 mantissa bits, 3 kind::f16 MMAs per fp32 product), fp32 accumulate"}
@@ -289,10 +362,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n = max(2, min(args.steps, 6))
+        n = max(2, min(args.steps, 6)) if args.config in ("cfg2", "cfg3") else 1      # ~5 / 46 / 160 s per frame
         frames, first, _ = make_workload(0, n + 1)
-        fps, dt = cpu_baseline(frames, first, n)
-        line = {"impl": "reference", "metric": "480p 5-object VOS frames/sec", "value": fps, "unit": "frames/s",
+        fps, dt, _ = cpu_baseline(frames, first, n)
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": n, "warmup": 1, "ms_per_step": 1000.0 * dt / n, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
@@ -337,7 +410,7 @@ def main():
     value = world * args.steps / (ms / 1000.0)
     e2e = world * args.steps / (ms_e2e / 1000.0)
 
-    line = {"metric": "480p 5-object VOS frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": st2.h2d // args.steps,
@@ -388,12 +461,18 @@ def main():
         line["roofline_all"] = roofs
         if "kmeans" in prof:
             line["kmeans_ms_per_step"] = prof["kmeans"]["ms"] / prof["frames"]
-        if world == 1 and not args.no_cpu_baseline:
-            fps, dt = cpu_baseline(frames.cpu(), first, args.cpu_frames)
+        if world == 1 and not args.no_cpu_baseline and args.cpu_frames > 0:
+            fps, dt, par = cpu_baseline(frames.cpu(), first, args.cpu_frames, model, device)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "%d predicted frames of the same clip after the GT frame (oracle port of "
                                               "the reference forward, torch CPU fp32 + scipy kmeans2), %.1f s"
                                               % (args.cpu_frames, dt)}
+            line["parity"] = par
+        elif world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "skipped: one frame of the CPU port at this size exceeds the bounded "
+                                              "sample (1080p: ~160 s per frame measured while generating "
+                                              "tests/golden/cfg5_1080p_k5_bank3.npz); pass --cpu-frames 1 to time it"}
         print(json.dumps(line))
     if dist:
         dist.barrier()

@@ -104,6 +104,78 @@ def test_480p_k5_vs_oracle(model, state_dict):
             prev_o, prev_e, prev_c, prev_g = eo, ee, mask, masks_g[-1]
 
 
+# observed x 1.5 (B200, round 2): see the [parity] lines these tests print
+CFG_BOUNDS = {
+    # name: (|engine - fp64| with pinned proxies, |engine - oracle fp32| with pinned proxies, argmax pixels differing)
+    "cfg4_720p_k10": (2.0e-2, 2.5e-2, 400),
+    "cfg5_1080p_k5_bank3": (2.0e-2, 2.5e-2, 400),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CFG_BOUNDS))
+def test_cfg4_cfg5_vs_oracle_fixture(model, name):
+    """BASELINE configs[3] (721x1281, 10 objects, frame 1) and configs[4] (1073x1921, 5 objects, frame 3 with a
+    three-frame bank) against the CPU oracle's committed vectors (tools/make_cfg_truth.py: the oracle needs minutes per
+    frame at these sizes).  The engine is fed the oracle's label maps and numpy seeds, and -- for the logit comparison --
+    pinned to the oracle's k-means proxies of the compared frame: k-means is a discrete step whose boundary rows flip
+    under 1e-6 perturbations (see the tool's docstring), which would otherwise drown a 1e-2 comparison in 0.1-0.3 jumps
+    that are a property of the algorithm.  A second run with the engine's own k-means is held to argmax agreement."""
+    import os
+    import torch.nn.functional as F
+    from aocb200.synth import make_clip
+    path = os.path.join(os.path.dirname(__file__), "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture %s not generated (python tools/make_cfg_truth.py)" % name)
+    f = np.load(path)
+    K, H, W, seed, n_pred = int(f["K"]), int(f["H"]), int(f["W"]), int(f["seed"]), int(f["n_pred"])
+    frames, labels = make_clip(seed, H, W, K, n_pred + 1)
+    dev = torch.device("cuda:0")
+    eng = model.engine()
+    gt = torch.tensor([K], device=dev)
+    l32, l64 = torch.from_numpy(f["logits_fp32"]), torch.from_numpy(f["logits_fp64"]).double()
+    n32 = float(f["oracle32_noise"])
+    want = torch.from_numpy(f["pred_fp32"])
+    res = {}
+    old = eng.use_graphs
+    eng.use_graphs = False                                  # the proxy pin is a plain-launch hook
+    try:
+        for pinned in (True, False):
+            _, emb, mem = model.forward_for_eval([[None, None]], [], [], None, None, frames[0:1].to(dev), [H, W], gt)
+            lab = labels[0].view(1, 1, H, W).to(dev)
+            refs, masks, prev_e, prev_m = [emb], [lab], emb, lab
+            for t in range(1, n_pred + 1):
+                np.random.seed(seed if t == 1 else 100 * seed + t)
+                eng.force_proxies = {k: f[k] for k in ("prox_cen", "prox_avg", "prox_ncen", "prox_navg")} \
+                    if (pinned and t == n_pred) else None
+                probs, emb, mem = model.forward_for_eval(mem, refs, masks, prev_e, prev_m, frames[t:t + 1].to(dev),
+                                                         [H, W], gt)
+                if t < n_pred:
+                    m = torch.from_numpy(f["fed"][t - 1]).view(1, 1, H, W).to(dev)
+                    refs.append(emb); masks.append(m)
+                    prev_e, prev_m = emb, m
+            le = eng.last_logits.clone().cpu()
+            pred = torch.argmax(probs[0], 0).to(torch.uint8).cpu()
+            res[pinned] = ((le.double() - l64).abs().max().item(), (le - l32).abs().max().item(), pred != want, le)
+    finally:
+        eng.force_proxies = None
+        eng.use_graphs = old
+    d64, d32, mism, le = res[True]
+    print("[parity] %s (oracle proxies pinned): |engine-fp64| %.3e  |engine-oracle fp32| %.3e  |oracle fp32-fp64| %.3e  "
+          "(logit range %.1f)  argmax differs from the oracle's at %d of %d px"
+          % (name, d64, d32, n32, l64.abs().max().item(), int(mism.sum()), mism.numel()))
+    b64, b32, bpx = CFG_BOUNDS[name]
+    assert d64 <= b64 and d32 <= b32, (d64, d32)
+    assert int(mism.sum()) <= bpx
+    if mism.any():                                          # every differing pixel is a float64 near-tie
+        up = F.interpolate(l64.float(), size=(H, W), mode="bilinear", align_corners=True)[0]
+        top2 = torch.topk(up, 2, dim=0)[0]
+        assert (top2[0] - top2[1])[mism].max().item() <= d64 + n32, "argmax differs away from a numerical tie"
+    o64, o32, omism, _ = res[False]
+    print("[parity] %s (engine's own k-means): |engine-fp64| %.3e  |engine-oracle fp32| %.3e  argmax-equal %.6f"
+          % (name, o64, o32, 1.0 - omism.float().mean().item()))
+    assert omism.float().mean().item() < 5e-3
+
+
 def _softmax_properties(probs, preds, first, K):
     seen = set(int(v) for v in torch.unique(first).tolist())
     for p, y in zip(probs, preds):

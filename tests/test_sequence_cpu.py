@@ -86,3 +86,62 @@ def test_run_sequence_matches_the_reference_eval_loop():
             assert len(a["ref_m"]) == len(b["ref_m"])
             for i, (x, y) in enumerate(zip(a["ref_m"], b["ref_m"])):
                 assert torch.equal(x, y), ("bank label map", c["seed"], t, i)
+
+
+class _ReplayTTA:
+    """the per-augmentation recording stub of tools/make_eval_loop_golden.py (call n = frame n // A, augmentation n % A)"""
+
+    def __init__(self, probs, A):
+        self.probs, self.A, self.calls, self.t = probs, A, [], 0
+
+    def forward_for_eval(self, memory, ref_e, ref_m, prev_e, prev_m, img, pred_size=None, gt_ids=None):
+        self.calls.append(dict(n_ref=len(ref_e), ref_m=[m.clone().long().view(m.shape[-2], m.shape[-1]) for m in ref_m],
+                               prev_m=None if prev_m is None else prev_m.clone().long().view(prev_m.shape[-2], prev_m.shape[-1]),
+                               img_hw=tuple(img.shape[-2:])))
+        n = self.t
+        self.t += 1
+        emb = torch.full((1, 4, 2, 2), float(n))
+        return (None if prev_e is None else self.probs[n // self.A, n % self.A][None].clone()), emb, memory
+
+
+def test_run_sequence_tta_matches_the_reference_eval_loop():
+    """tests/golden/eval_loop_tta_trace.pt: the REFERENCE's own loop (eval_manager_mm.py:160-394, unmodified) with
+    test-time augmentation -- flip only; flip with an object joining at a ground-truth frame; two scales x flip with a
+    join on a memory frame; three scales without flip.  run_sequence_tta must hand the model the same label maps on every
+    call of every augmentation stream (incl. the unflipped confident mask in the mirrored stream's bank, the last
+    augmentation's entropy, the seen-label list growing between augmentations) and save the same label maps."""
+    import os
+    import torch.nn.functional as F
+    from aocb200.sequence import run_sequence_tta
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "eval_loop_tta_trace.pt"))
+    assert len(cases) == 4
+    for c in cases:
+        augs = [(sz, fl) for sz in c["sizes"] for fl in ((False, True) if c["flip"] else (False,))]
+        A = len(augs)
+        samples = []
+        for t in range(c["T"]):
+            row = []
+            for (h, w), fl in augs:
+                lab = c["labels"].get(t)
+                if lab is not None:
+                    if (h, w) != (c["H"], c["W"]):
+                        lab = F.interpolate(lab[None, None].float(), size=(h, w), mode="nearest")[0, 0].long()
+                    if fl:
+                        lab = torch.flip(lab, dims=[1])
+                row.append(dict(img=torch.zeros(1, 3, h, w), label=lab, flip=fl, size=(c["H"], c["W"])))
+            samples.append(row)
+        stub = _ReplayTTA(c["probs"], A)
+        preds = run_sequence_tta(stub, samples, c["K"], mem_every=c["mem_every"], unc_ratio=c["unc_ratio"])
+        assert len(preds) == len(c["saved"]) == c["T"] - 1
+        for t, (a, b) in enumerate(zip(preds, c["saved"])):
+            assert torch.equal(a.long(), b), ("saved label map", c["seed"], t + 1)
+        assert len(stub.calls) == len(c["calls"]) == c["T"] * A
+        for n, (a, b) in enumerate(zip(stub.calls, c["calls"])):
+            assert a["n_ref"] == b["n_ref"], ("bank length", c["seed"], n)
+            assert a["img_hw"] == b["img_hw"]
+            assert (a["prev_m"] is None) == (b["prev_m"] is None)
+            if a["prev_m"] is not None:
+                assert torch.equal(a["prev_m"], b["prev_m"]), ("previous mask", c["seed"], n)
+            assert len(a["ref_m"]) == len(b["ref_m"]), ("bank masks", c["seed"], n)
+            for i, (x, y) in enumerate(zip(a["ref_m"], b["ref_m"])):
+                assert torch.equal(x, y), ("bank label map", c["seed"], n, i)

@@ -5,7 +5,11 @@ recording stub in place of the network, and stores what the loop handed to the m
 maps incl. the label-125 "confident" masks, previous masks, bank length) and the label maps it saved.
 tests/test_sequence_cpu.py replays run_sequence on the same stub outputs and compares.  Build container only.
 
-    python tools/make_eval_loop_golden.py          # -> tests/golden/eval_loop_trace.pt
+    python tools/make_eval_loop_golden.py          # -> tests/golden/eval_loop_trace.pt, eval_loop_tta_trace.pt
+
+The second file pins aocb200/sequence.py::run_sequence_tta (TEST_FLIP / TEST_MULTISCALE, eval_manager_mm.py:195-361) the
+same way: the dataset hands the loop several augmented samples per frame (plain / mirrored, two scales), the stub
+returns different probabilities per augmentation, and every label map the loop handed back or saved is recorded.
 """
 import importlib
 import os
@@ -63,6 +67,63 @@ class SeqDataset(torch.utils.data.Dataset):
         return [s]
 
 
+class TTAStub(RecordingStub):
+    """per-augmentation probabilities: call n = frame n // A, augmentation n % A"""
+
+    def __init__(self, probs, A):
+        super().__init__(probs)
+        self.A = A
+
+    def forward_for_eval(self, memory, ref_e, ref_m, prev_e, prev_m, img, pred_size=None, gt_ids=None):
+        self.calls.append(dict(n_ref=len(ref_e), ref_m=[m.clone().long().view(m.shape[-2], m.shape[-1]) for m in ref_m],
+                               prev_m=None if prev_m is None else prev_m.clone().long().view(prev_m.shape[-2], prev_m.shape[-1]),
+                               img_hw=tuple(img.shape[-2:])))
+        n = self.t
+        self.t += 1
+        emb = torch.full((1, 4, 2, 2), float(n))
+        return (None if prev_e is None else self.probs[n // self.A, n % self.A][None].clone()), emb, memory
+
+
+def resize_label(lab, size):
+    return torch.nn.functional.interpolate(lab[None, None].float(), size=size, mode="nearest")[0, 0].long()
+
+
+def tta_augs(c):
+    """(scale size, flip) per augmentation in the order of MultiRestrictSize(+flip): custom_transforms.py:433-462"""
+    return [(sz, fl) for sz in c["sizes"] for fl in ((False, True) if c["flip"] else (False,))]
+
+
+class TTADataset(SeqDataset):
+    def __init__(self, name, c):
+        super().__init__(name, c["T"], c["H"], c["W"], c["labels"])
+        self.c = c
+
+    def __getitem__(self, i):
+        out = []
+        for (h, w), fl in tta_augs(self.c):
+            s = {"current_img": torch.zeros(3, h, w)}
+            if i in self.labels:
+                lab = self.labels[i]
+                if (h, w) != (self.H, self.W):
+                    lab = resize_label(lab, (h, w))
+                if fl:
+                    lab = torch.flip(lab, dims=[1])
+                s["current_label"] = lab.to(torch.uint8).view(1, h, w)
+            s["meta"] = {"seq_name": self.seq_name, "frame_num": self.T, "obj_num": 3, "obj_list": [0, 1, 2, 3],
+                         "current_name": "%05d.jpg" % i, "height": self.H, "width": self.W, "flip": fl}
+            out.append(s)
+        return out
+
+
+def tta_case(seed, T, H, W, K, mem_every, unc_ratio, absent, join_at, sizes, flip):
+    c = case(seed, T, H, W, K, mem_every, unc_ratio, absent, join_at)
+    A = len(sizes) * (2 if flip else 1)
+    g = torch.Generator().manual_seed(seed + 7)
+    c["probs"] = torch.softmax(torch.randn(T, A, K + 1, H, W, generator=g) * 2.0, dim=2)
+    c["sizes"], c["flip"] = sizes, flip
+    return c
+
+
 def case(seed, T, H, W, K, mem_every, unc_ratio, absent, join_at):
     g = torch.Generator().manual_seed(seed + 100)
     first = torch.randint(0, K + 1, (H, W), generator=g)
@@ -76,7 +137,7 @@ def case(seed, T, H, W, K, mem_every, unc_ratio, absent, join_at):
                 probs=stub_probs(seed, T, K + 1, H, W))
 
 
-def run_reference_loop(c):
+def run_reference_loop(c, tta=False):
     load_reference()
     sys.modules["matplotlib.pyplot"].rcParams = {}
     em = importlib.import_module("networks.engine.eval_manager_mm")
@@ -85,8 +146,12 @@ def run_reference_loop(c):
     em.zip_folder = lambda *a, **k: None
     ev = object.__new__(em.Evaluator)
     ev.cfg = types.SimpleNamespace(BLOCK_NUM=2, TEST_WORKERS=0)
-    ev.model = RecordingStub(c["probs"])
-    ev.dataset = [SeqDataset("seq", c["T"], c["H"], c["W"], c["labels"])]
+    if tta:
+        ev.model = TTAStub(c["probs"], len(tta_augs(c)))
+        ev.dataset = [TTADataset("seq", c)]
+    else:
+        ev.model = RecordingStub(c["probs"])
+        ev.dataset = [SeqDataset("seq", c["T"], c["H"], c["W"], c["labels"])]
     ev.mem_every, ev.unc_ratio, ev.gpu = c["mem_every"], c["unc_ratio"], 0
     ev.result_root = ev.source_folder = "/tmp/eval_loop_golden"
     ev.zip_dir = "/tmp/eval_loop_golden.zip"
@@ -114,6 +179,22 @@ def main():
         out.append(dict(c, calls=calls, saved=saved))
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+    tta = [tta_case(11, 7, 6, 8, 3, 2, 0.8, 2, None, [(6, 8)], True),                 # flip only, an id never appears
+           tta_case(12, 8, 6, 8, 3, 2, 0.8, 2, 3, [(6, 8)], True),                    # flip, the id joins with ground truth at frame 3
+           tta_case(13, 7, 6, 8, 3, 3, 0.9, 3, 3, [(6, 8), (9, 11)], True),           # two scales x flip, join on a memory frame
+           tta_case(14, 6, 5, 7, 2, 2, 0.7, 9, None, [(5, 7), (7, 9), (4, 6)], False)]  # three scales, no flip
+    out = []
+    for c in tta:
+        calls, saved = run_reference_loop(c, tta=True)
+        A = len(tta_augs(c))
+        assert len(calls) == c["T"] * A and len(saved) == c["T"] - 1
+        n125 = sum(int((m == 125).sum()) for call in calls for m in call["ref_m"])
+        print("tta case seed %d: %d augmentations, %d calls, label-125 pixels handed to the model %d"
+              % (c["seed"], A, len(calls), n125))
+        out.append(dict(c, calls=calls, saved=saved))
+    out_tta = os.path.join(ROOT, "tests", "golden", "eval_loop_tta_trace.pt")
+    torch.save(out, out_tta)
+    print("wrote", out_tta, os.path.getsize(out_tta), "bytes")
 
 
 if __name__ == "__main__":
