@@ -556,29 +556,30 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 }
             }
             if (SK) {
-                // ---- split-K: the slice that arrives LAST at the tile's counter adds the ksplit partial tiles in slice
-                // order (deterministic whichever slice that is), applies bias / residual / ReLU and writes y -- the
-                // separate finish kernel (65 launches per frame on the 31x54 backbone maps) is gone.  The other slices'
-                // partial sums are read with ld.global.cg: they were written by other SMs during this launch.
-                int* flag = reinterpret_cast<int*>(smem + Cfg::STAT_OFF);
-                const int tile_id = t / p.ksplit;
+                // ---- split-K finish, fused (the separate finish kernel -- 65 launches per frame on the 31x54 backbone maps --
+                // is gone).  Every K slice of a tile runs on its own CTA at the same time (the launcher splits only when
+                // tiles x slices <= SMs, one work item per CTA), so the slices MEET at the tile's counter: each writes its
+                // partial tile, arrives, waits until all `ksplit` slices have arrived, and then finishes its share of the
+                // tile's 128 pixel rows -- the partial tiles are added in slice order (deterministic), bias / residual /
+                // ReLU applied, y written.  The other slices' sums are read with ld.global.cg (written by other SMs during
+                // this launch).  A second round of arrivals tells the last slice to clear the counter for the next launch.
+                int* cnt = p.ws_cnt + t / p.ksplit;
                 __threadfence();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (threadIdx.x == 256) {
-                    const int old = atomicAdd(p.ws_cnt + tile_id, 1);
-                    const int last = old == p.ksplit - 1;
-                    if (last) p.ws_cnt[tile_id] = 0;                 // every slice has arrived: ready for the next launch
-                    *flag = last;
+                    atomicAdd(cnt, 1);
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                    } while (v < p.ksplit);
+                    __threadfence();
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                const bool last = *flag != 0;
-                asm volatile("bar.sync 2, 256;" ::: "memory");          // (the flag word is rewritten by the next item)
-                if (last) {
-                    __threadfence();
+                {
                     const size_t Mtot = (size_t)p.N * p.Ho * p.Wo;
-                    const int i0 = threadIdx.x - 256;                    // 0..255 over 128 pixels x (TN / 4) float4 columns
                     constexpr int C4 = TN / 4;
-                    for (int i = i0; i < C2_BM * C4; i += 256) {
+                    const int m_lo = C2_BM * tl.ks / p.ksplit, m_hi = C2_BM * (tl.ks + 1) / p.ksplit;
+                    for (int i = m_lo * C4 + (threadIdx.x - 256); i < m_hi * C4; i += 256) {
                         const int m = i / C4, c = (i - m * C4) * 4;
                         const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
                         const int co = tl.n0 + c;
@@ -598,6 +599,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         *reinterpret_cast<float4*>(p.y + pix * p.ldy + co) = a;
                     }
                 }
+                asm volatile("bar.sync 2, 256;" ::: "memory");          // every thread of this slice has read the partial sums
+                if (threadIdx.x == 256 && atomicAdd(cnt, 1) == 2 * p.ksplit - 1) *cnt = 0;
             }
             if (!SK && p.tile_stats) {
                 // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels

@@ -105,14 +105,33 @@ __global__ void pack_tc_image_f16_kernel(const float* __restrict__ x, int R, int
     }
 }
 
-// MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test)
+// Bank-sharded matching of ONE sequence on several GPUs: rank r contracts the queries with its range of
+// bank row blocks only; min over bank rows = min over the ranks' partial minima (associative and commutative: the
+// result is bit-identical to the single-GPU one).  The exchange is part of the matching kernel: as soon as a CTA has
+// the per-object minima of its 128 query rows it stores them into its slot of every peer's receive buffer (plain
+// stores to peer-mapped memory, i.e. NVLink writes), fences at system scope and bumps the peer's arrival counter --
+// the transfer of a tile overlaps the contraction of the tiles still running; no collective call, no extra launch.
+constexpr int MATCH_MAX_PEERS = 8;
+struct MatchPeers {
+    float* recv[MATCH_MAX_PEERS];        // peer p's receive slot for THIS rank, parity 0: [HW][O]
+    unsigned* flag[MATCH_MAX_PEERS];     // peer p's arrival counter, parity 0 (parity 1: + 16 words)
+    int n;                               // number of peers (world - 1); 0 = not sharded
+    const unsigned* epoch;               // device word: frames exchanged so far; parity = epoch & 1 (double-buffered slots:
+                                         // a rank can run at most one frame ahead of a peer, see DESIGN)
+    long long par_stride;                // floats between the parity-0 and parity-1 slots (same layout on every rank)
+};
+
+// MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test);
+// MODE 2: MODE 0 restricted to the row blocks [rb_begin, rb_end) (grid.y = 1) + the peer exchange above.
+// Simg / r2 start at row block img_rb0.
 template <int MODE, bool F16>
 __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restrict__ Qimg,
                                                           const uint8_t* __restrict__ Simg,
                                                           const float* __restrict__ q2, const float* __restrict__ r2,
-                                                          const int* __restrict__ meta, int O, int HW, int nrb_total,
+                                                          const int* __restrict__ meta, int O, int HW, int rb_begin,
+                                                          int rb_end, int img_rb0,
                                                           int nsplit, float* __restrict__ mins, float* __restrict__ C,
-                                                          int ldc, uint32_t lbo, uint32_t sbo) {
+                                                          int ldc, uint32_t lbo, uint32_t sbo, MatchPeers peers) {
     constexpr int TC_KS = MatchFmt<F16>::KS;
     constexpr uint32_t A_BYTES = MatchFmt<F16>::A_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -125,8 +144,13 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int qt = blockIdx.x, sp = blockIdx.y;
-    const int rb0 = (int)((long long)nrb_total * sp / nsplit);
-    const int rb1 = (int)((long long)nrb_total * (sp + 1) / nsplit);
+    long long par_off = 0;
+    if (MODE == 2) {                                       // this frame's parity: read at run time, a captured graph follows it
+        par_off = (long long)(*peers.epoch & 1u) * peers.par_stride;
+        mins += par_off;
+    }
+    const int rb0 = rb_begin + (int)((long long)(rb_end - rb_begin) * sp / nsplit);
+    const int rb1 = rb_begin + (int)((long long)(rb_end - rb_begin) * (sp + 1) / nsplit);
     const uint32_t bar0 = smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (NST + s); };
@@ -134,7 +158,7 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
     auto TFULL = [&](int s) { return bar0 + 8u * (2 * NST + 1 + s); };
     auto TEMPTY = [&](int s) { return bar0 + 8u * (2 * NST + 3 + s); };
 
-    if (threadIdx.x <= O && MODE == 0) seg[threadIdx.x] = meta[MAXO_ + threadIdx.x];
+    if (threadIdx.x <= O && MODE != 1) seg[threadIdx.x] = meta[MAXO_ + threadIdx.x];
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
         mbar_init(A_FULL, 1);
@@ -163,8 +187,8 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                 for (int ks = 0; ks < TC_KS; ++ks) {
                     mbar_wait(EMPTY(stage), phase ^ 1u);
                     mbar_arrive_expect_tx(FULL(stage), B_STAGE);
-                    bulk_g2s(smem_u32(sB) + stage * B_STAGE, Simg + ((size_t)rb * TC_KS + ks) * B_STAGE, B_STAGE,
-                             FULL(stage));
+                    bulk_g2s(smem_u32(sB) + stage * B_STAGE, Simg + ((size_t)(rb - img_rb0) * TC_KS + ks) * B_STAGE,
+                             B_STAGE, FULL(stage));
                     if (++stage == NST) { stage = 0; phase ^= 1u; }
                 }
         }
@@ -215,16 +239,16 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const int qi = qt * QB + row;
-        const float qq = (MODE == 0 && qi < HW) ? __ldg(q2 + qi) : 0.f;
+        const float qq = (MODE != 1 && qi < HW) ? __ldg(q2 + qi) : 0.f;
         int as = 0;
         uint32_t aphase = 0;
         int cur = 0;
         float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;   // four independent chains of the running minimum
-        if (MODE == 0) {
+        if (MODE != 1) {
             while (cur < O - 1 && rb0 * RBK >= seg[cur + 1]) ++cur;
         }
         for (int rb = rb0; rb < rb1; ++rb) {
-            if (MODE == 0) {
+            if (MODE != 1) {
                 if (rb * RBK >= seg[cur + 1]) {   // crossed into the next object's segment: flush
                     if (qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = fminf(fminf(m0, m1), fminf(m2, m3));
                     m0 = m1 = m2 = m3 = INFINITY;
@@ -240,8 +264,8 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                 tmem_ld32(t0 + c0, v);
                 tmem_ld32(t0 + c0 + 32, v + 32);
                 tmem_ld_wait();
-                if (MODE == 0) {
-                    const float4* rr = reinterpret_cast<const float4*>(r2 + (size_t)rb * RBK + c0);
+                if (MODE != 1) {
+                    const float4* rr = reinterpret_cast<const float4*>(r2 + (size_t)(rb - img_rb0) * RBK + c0);
 #pragma unroll
                     for (int j4 = 0; j4 < 16; ++j4) {
                         float4 r4 = __ldg(rr + j4);
@@ -261,7 +285,23 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
             as ^= 1;
             if (as == 0) aphase ^= 1u;
         }
-        if (MODE == 0 && rb1 > rb0 && qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = fminf(fminf(m0, m1), fminf(m2, m3));
+        if (MODE != 1 && rb1 > rb0 && qi < HW) mins[((size_t)sp * HW + qi) * O + cur] = fminf(fminf(m0, m1), fminf(m2, m3));
+        if (MODE == 2) {
+            // ---- peer exchange: this CTA's [rows][O] block of the local slot (objects outside this rank's row range keep
+            // the +inf the slot was filled with) goes to the same place in every peer's slot for this rank
+            asm volatile("bar.sync 3, 128;" ::: "memory");                  // the block is complete (the four epilogue warps)
+            const int te = threadIdx.x - 128;
+            const int nval = min(QB, HW - qt * QB) * O;
+            const size_t off = (size_t)qt * QB * O;
+            for (int pi = 0; pi < peers.n; ++pi) {
+                float* dst = peers.recv[pi] + par_off + off;
+                for (int i = te; i < nval; i += 128) dst[i] = __ldcg(mins + off + i);
+            }
+            __threadfence_system();
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+            if (te == 0)
+                for (int pi = 0; pi < peers.n; ++pi) atomicAdd_system(peers.flag[pi] + (par_off ? 16 : 0), 1u);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -336,7 +376,7 @@ static int pick_splits(int nqt, int nrb) {
     return s;
 }
 
-static PerDeviceOnce g_attr0, g_attr1;
+static PerDeviceOnce g_attr0, g_attr1, g_attr2;
 
 }  // namespace aoc
 
@@ -435,16 +475,182 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
         }
         dim3 grid(nqt, nsplit);
         if (f16)
-            match_tc_kernel<0, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb, nsplit,
-                                                                                 mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
+            match_tc_kernel<0, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, 0, nrb, 0,
+                                                                                 nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES,
+                                                                                 MatchPeers{});
         else
-            match_tc_kernel<0, false><<<grid, 256, MatchFmt<false>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, nrb,
-                                                                                   nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES);
+            match_tc_kernel<0, false><<<grid, 256, MatchFmt<false>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, 0, nrb, 0,
+                                                                                   nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES,
+                                                                                   MatchPeers{});
         if (nsplit > 1) min_over_splits_kernel<<<cdiv(n, 256), 256, 0, stream>>>(mins, n, nsplit);
     }
     rc = aoc_global_match_finalize_f32(mins, meta_dev, bias, HW, O, out, stream);
     if (rc) return rc;
     return launch_status("aoc_global_match_tc");
+}
+
+// ---------------------------------------------------------------------------------------------- bank-sharded matching
+namespace aoc {
+// Per-rank exchange area (one cudaMalloc'ed, IPC-exported allocation per rank, see peer.cu):
+//   [0, 256)                 arrival counters: flag[parity] at byte 64 * parity (monotone, bumped by the peers' CTAs)
+//   [256, ...)               recv[parity][world][cap_hw][MAXO] floats: slot (parity, g) = rank g's partial minima
+// Local state (device, 64 bytes, zeroed once): {epoch, expected[2], done counter}.
+__host__ __device__ inline size_t match_slot_floats(int cap_hw) { return (size_t)cap_hw * MAXO_; }
+
+struct ShardState { unsigned epoch, expected[2], done; };
+
+// waits for every peer's partial minima of this frame, reduces over the ranks, then the same tail as
+// global_match_finalize_kernel (matching.py:83-90, :2505-2508).  The last block advances the epoch.
+__global__ void __launch_bounds__(256) match_sharded_finalize_kernel(const float* __restrict__ recv_all /*[2][world][cap][MAXO]*/,
+                                                                    const unsigned* __restrict__ flags, ShardState* st,
+                                                                    int world, int cap_hw, unsigned add_expected,
+                                                                    const int* __restrict__ meta,
+                                                                    const float* __restrict__ bias, int HW, int O,
+                                                                    float* __restrict__ out) {
+    __shared__ unsigned s_par;
+    if (threadIdx.x == 0) {
+        const unsigned e = st->epoch;
+        const unsigned par = e & 1u;
+        const unsigned want = st->expected[par] + add_expected;
+        const unsigned* f = flags + 16 * par;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        } while ((int)(v - want) < 0);
+        s_par = par;
+    }
+    __syncthreads();
+    const unsigned par = s_par;
+    const float* base = recv_all + (size_t)par * world * match_slot_floats(cap_hw);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < HW) {
+        if (meta[2 * MAXO_ + 2] == 0) {
+            for (int o = 0; o < O; ++o) out[(size_t)p * O + o] = 1.0f;
+        } else {
+            float m[MAXO_];
+            float m1 = INFINITY, m2 = INFINITY;
+            int a1 = -1;
+            for (int o = 0; o < O; ++o) {
+                float v = INFINITY;
+                if (meta[o] > 0)
+                    for (int g = 0; g < world; ++g)
+                        v = fminf(v, __ldcg(base + (size_t)g * match_slot_floats(cap_hw) + (size_t)p * O + o));
+                m[o] = v;
+                if (v < m1) { m2 = m1; m1 = v; a1 = o; }
+                else if (v < m2) { m2 = v; }
+            }
+            for (int o = 0; o < O; ++o) {
+                const float other = (o == a1) ? m2 : m1;
+                const float d = fminf(m[o], other + AOC_WRONG_LABEL_PAD);
+                out[(size_t)p * O + o] = sig2(d + __ldg(bias + o));
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&st->done, 1u);
+        if (done == gridDim.x - 1) {
+            st->expected[par] += add_expected;
+            st->done = 0;
+            __threadfence();
+            st->epoch += 1;
+        }
+    }
+}
+
+}  // namespace aoc
+
+extern "C" size_t aoc_match_shard_area_bytes(int world, int cap_hw) {
+    return 256 + (size_t)2 * world * match_slot_floats(cap_hw) * sizeof(float);
+}
+
+// Row blocks [nrb * rank / world, nrb * (rank + 1) / world) of the object-sorted bank are this rank's share.
+extern "C" int aoc_match_shard_range(int rows_padded, int rank, int world, int* rb_begin, int* rb_end) {
+    AOC_CHECK_ARG(rows_padded % RBK == 0 && world >= 1 && rank >= 0 && rank < world && rb_begin && rb_end, "bad args");
+    const int nrb = rows_padded / RBK;
+    *rb_begin = (int)((long long)nrb * rank / world);
+    *rb_end = (int)((long long)nrb * (rank + 1) / world);
+    return AOC_OK;
+}
+
+namespace aoc {
+__global__ void fill_slot_kernel(float* base, long long par_stride, const unsigned* epoch, float v, long long n) {
+    float* p = base + (long long)(*epoch & 1u) * par_stride;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+}  // namespace aoc
+
+// aoc_global_match_tc for ONE sequence whose bank is sharded over `world` GPUs (one process per GPU, all running the same
+// frames in lockstep).  areas[g] = rank g's exchange area (aoc_match_shard_area_bytes, allocated / exported / opened with
+// the aoc_peer_* calls) as mapped into this process, areas[rank] the local one; state = 64 zeroed device bytes (local).
+// The call contracts q with this rank's row-block range only, ships the partial minima to every peer from inside the
+// matching kernel and reduces the `world` partial results; `out` is bit-identical to aoc_global_match_tc's on every rank.
+extern "C" int aoc_global_match_tc_sharded(const float* q, int HW, const float* S, const float* r2, const int* meta_dev,
+                                           int rows_padded, const float* bias, int O, int rank, int world,
+                                           void* const* areas, int cap_hw, void* state, void* workspace,
+                                           size_t ws_bytes, float* out, cudaStream_t stream) {
+    AOC_CHECK_ARG(q && S && r2 && meta_dev && bias && workspace && out && areas && state, "null pointer");
+    AOC_CHECK_ARG(O >= 1 && O <= MAXO_ && HW > 0 && HW <= cap_hw && rows_padded % RBK == 0, "bad dims");
+    AOC_CHECK_ARG(world >= 2 && world <= MATCH_MAX_PEERS + 1 && rank >= 0 && rank < world, "bad rank / world");
+    AOC_CHECK_ARG(ws_bytes >= aoc_global_match_tc_workspace_bytes(HW, rows_padded), "workspace too small");
+    uint8_t* ws = (uint8_t*)workspace;
+    size_t imgq = aoc_tc_image_bytes(HW, TC_K, QB), imgs = aoc_tc_image_bytes(rows_padded > 0 ? rows_padded : 1, TC_K, RBK);
+    uint8_t* Qimg = ws;
+    uint8_t* Simg = ws + imgq;
+    float* q2 = (float*)(ws + imgq + imgs);
+    float* r2c = q2 + ((HW + QB + 3) & ~3);
+    float* mu = r2c + (rows_padded + RBK);
+    float* part = mu + 128;
+    const int nqt = cdiv(HW, QB), nb = cdiv(HW, MU_SLAB);
+    int rb_lo = 0, rb_hi = 0;
+    aoc_match_shard_range(rows_padded, rank, world, &rb_lo, &rb_hi);
+    col_sum_partial_kernel<<<nb, 256, 0, stream>>>(q, HW, MU_SLAB, part);
+    col_mean_final_kernel<<<1, 128, 0, stream>>>(part, nb, HW, mu);
+    const bool f16 = g_match_f16 != 0;
+    int rc = pack_centered(q, HW, QB, mu, nullptr, Qimg, f16, stream);
+    if (rc) return rc;
+    centered_sqnorm_kernel<<<cdiv((long long)HW * 32, 256), 256, 0, stream>>>(q, HW, mu, nullptr, q2);
+    const long long my_rows = (long long)(rb_hi - rb_lo) * RBK;
+    if (my_rows > 0) {                                   // only this rank's share of the bank is packed
+        const float* S0 = S + (size_t)rb_lo * RBK * 100;
+        rc = pack_centered(S0, my_rows, RBK, mu, r2 + (size_t)rb_lo * RBK, Simg, f16, stream);
+        if (rc) return rc;
+        centered_sqnorm_kernel<<<cdiv(my_rows * 32, 256), 256, 0, stream>>>(S0, (int)my_rows, mu, r2 + (size_t)rb_lo * RBK, r2c);
+    }
+    ShardState* st = (ShardState*)state;
+    const size_t slot = match_slot_floats(cap_hw);
+    MatchPeers pr = {};
+    pr.n = 0;
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) continue;
+        AOC_CHECK_ARG(areas[g], "peer area not mapped");
+        pr.recv[pr.n] = (float*)((char*)areas[g] + 256) + (size_t)rank * slot;       // my slot on peer g, parity 0
+        pr.flag[pr.n] = (unsigned*)areas[g];
+        ++pr.n;
+    }
+    pr.epoch = &st->epoch;
+    pr.par_stride = (long long)world * slot;
+    float* local_slot = (float*)((char*)areas[rank] + 256) + (size_t)rank * slot;     // parity 0
+    const long long n = (long long)HW * O;
+    fill_slot_kernel<<<cdiv(n, 1024), 256, 0, stream>>>(local_slot, pr.par_stride, &st->epoch, INFINITY, n);
+    if (g_attr2.first()) {
+        cudaFuncSetAttribute(match_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<false>::SMEM);
+        cudaFuncSetAttribute(match_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<true>::SMEM);
+    }
+    dim3 grid(nqt, 1);
+    if (f16)
+        match_tc_kernel<2, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, rb_lo, rb_hi,
+                                                                             rb_lo, 1, local_slot, nullptr, 0, LBO_BYTES,
+                                                                             SBO_BYTES, pr);
+    else
+        match_tc_kernel<2, false><<<grid, 256, MatchFmt<false>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, rb_lo,
+                                                                               rb_hi, rb_lo, 1, local_slot, nullptr, 0,
+                                                                               LBO_BYTES, SBO_BYTES, pr);
+    match_sharded_finalize_kernel<<<cdiv(HW, 256), 256, 0, stream>>>(
+        (const float*)((char*)areas[rank] + 256), (const unsigned*)areas[rank], st, world, cap_hw,
+        (unsigned)((world - 1) * nqt), meta_dev, bias, HW, O, out);
+    return launch_status("aoc_global_match_tc_sharded");
 }
 
 // Self-test of the tcgen05 pipeline: C[M][N] = A[M][K] * B[N][K]^T, K <= 104 (zero padded), M % 128 == 0, N % 256 == 0.
@@ -466,7 +672,7 @@ extern "C" int aoc_gemm_tf32x3_test(const float* A, const float* B, float* C, in
     }
     dim3 grid(M / QB, 1);
     uint32_t lbo = variant == 1 ? SBO_BYTES : LBO_BYTES, sbo = variant == 1 ? LBO_BYTES : SBO_BYTES;
-    match_tc_kernel<1, false><<<grid, 256, SMEM_MATCH, stream>>>(Ai, Bi, nullptr, nullptr, nullptr, 1, M, N / RBK, 1, nullptr, C,
-                                                         N, lbo, sbo);
+    match_tc_kernel<1, false><<<grid, 256, SMEM_MATCH, stream>>>(Ai, Bi, nullptr, nullptr, nullptr, 1, M, 0, N / RBK, 0, 1, nullptr,
+                                                         C, N, lbo, sbo, MatchPeers{});
     return launch_status("aoc_gemm_tf32x3_test");
 }

@@ -174,6 +174,7 @@ class Engine:
         self.debug = {}
         self.keep_debug = False
         self.force_proxies = None       # test hook, see _apply_forced_proxies
+        self.shard = None               # bank sharding over several GPUs (aocb200/shard.py::setup_bank_sharding)
         # tensor-core (tcgen05, 3xTF32) kernels vs the fp32 SIMT kernels; both are CUDA, same results to ~1e-6 relative
         tc = os.environ.get("AOCB200_TC", "1") != "0"
         self.tc_conv = tc and os.environ.get("AOCB200_TC_CONV", "1") != "0"
@@ -559,7 +560,15 @@ class Engine:
         S, r2, meta = ix["S"], ix["r2"], ix["meta"]
         # --- pixel-level global matching (matching.py:2384)
         g = self.empty(hw * O)
-        if self.tc_match and rows > 0:
+        if self.shard is not None:
+            # one sequence over several GPUs: this rank's share of the bank rows, partial minima exchanged by the kernel
+            sh = self.shard
+            assert self.tc_match and rows > 0 and hw <= sh["cap_hw"]
+            nws2 = L.global_match_tc_workspace_bytes(hw, rows)
+            L.global_match_tc_sharded(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), rows, bias.data_ptr(), O,
+                                      sh["rank"], sh["world"], sh["areas"], sh["cap_hw"], sh["state"].data_ptr(),
+                                      self.ws("gm_tc", nws2).data_ptr(), nws2, g.data_ptr(), st)
+        elif self.tc_match and rows > 0:
             nws2 = L.global_match_tc_workspace_bytes(hw, rows)
             L.global_match_tc(q.ptr, hw, S.data_ptr(), r2.data_ptr(), meta.data_ptr(), rows, bias.data_ptr(), O,
                               self.ws("gm_tc", nws2).data_ptr(), nws2, g.data_ptr(), st)

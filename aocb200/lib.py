@@ -52,7 +52,8 @@ class AocError(RuntimeError):
 KERNELS_PER_CALL = {
     "aoc_channel_stats_f32": 2, "aoc_affine_stats_nc_f32": 2, "aoc_bank_index_build": 4, "aoc_global_match_simt_f32": 2, "aoc_global_match_tc": 10,
     "aoc_head_pool_f32": 2, "aoc_dyn_logits_f32": 2, "aoc_gemm_tf32x3_test": 3,
-    "aoc_version": 0, "aoc_check_device": 0, "aoc_last_error_string": 0, "aoc_set_option": 0, "aoc_conv_tiles_per_image": 0, "aoc_conv_trace": 0,
+    "aoc_global_match_tc_sharded": 9, "aoc_peer_alloc": 0, "aoc_peer_free": 0, "aoc_peer_export": 0, "aoc_peer_open": 0,
+    "aoc_peer_close": 0, "aoc_match_shard_range": 0, "aoc_version": 0, "aoc_check_device": 0, "aoc_last_error_string": 0, "aoc_set_option": 0, "aoc_conv_tiles_per_image": 0, "aoc_conv_trace": 0,
 }
 
 

@@ -184,8 +184,11 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
     from aocb200.lib import lib
     l0 = lib().launches
     e0.record()
+    walls = []
     for _ in range(steps):
+        w0 = time.perf_counter()
         st.step()
+        walls.append(time.perf_counter() - w0)
     e1.record()
     torch.cuda.synchronize()
     if dist:
@@ -193,6 +196,10 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
     gc.enable()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
+    if host_io:        # diagnostic (stderr): host wall time per step of the end-to-end run -- a single stalled step shows here
+        ws = sorted(walls)
+        print("e2e host wall per step: median %.2f ms, max %.2f ms (step %d), sum %.1f ms; device %.1f ms"
+              % (1e3 * ws[len(ws) // 2], 1e3 * ws[-1], walls.index(ws[-1]), 1e3 * sum(walls), ms), file=sys.stderr)
     if dist:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -192,6 +192,28 @@ int aoc_global_match_simt_f32(const float* q, int HW, const float* S, const floa
 size_t aoc_global_match_tc_workspace_bytes(int HW, int rows_padded);
 int aoc_global_match_tc(const float* q, int HW, const float* S, const float* r2, const int* meta_dev, int rows_padded,
                         const float* bias, int O, void* workspace, size_t ws_bytes, float* out, cudaStream_t stream);
+/* ---- bank-sharded matching of ONE sequence over several GPUs (the op is matching.py:2384-2516, the bank
+ * growth eval_manager_mm.py:309-312).  One process per GPU, all ranks run the same frames; rank r contracts the queries
+ * with row blocks [nrb*r/world, nrb*(r+1)/world) of the object-sorted bank only, and the min over ranks -- associative,
+ * so `out` is bit-identical to aoc_global_match_tc's -- is exchanged from INSIDE the matching kernel: each CTA stores
+ * the minima of its 128 query rows into its slot of every peer's exchange area (peer-mapped memory: NVLink writes),
+ * fences at system scope and bumps the peer's arrival counter; a finalize kernel waits for the counters and reduces.
+ * No collective call and no host synchronisation per frame.
+ * areas[g]: rank g's exchange area (aoc_match_shard_area_bytes(world, cap_hw) bytes from aoc_peer_alloc, exported with
+ * aoc_peer_export, mapped with aoc_peer_open; areas[rank] = the local allocation) -- a HOST array of `world` pointers;
+ * state: 64 zeroed device bytes owned by this rank; HW <= cap_hw. */
+#define AOC_PEER_HANDLE_BYTES 64
+int aoc_peer_alloc(size_t bytes, void** ptr_out);
+int aoc_peer_free(void* ptr);
+int aoc_peer_export(void* ptr, void* handle_out);
+int aoc_peer_open(const void* handle, void** ptr_out);
+int aoc_peer_close(void* ptr);
+size_t aoc_match_shard_area_bytes(int world, int cap_hw);
+int aoc_match_shard_range(int rows_padded, int rank, int world, int* rb_begin, int* rb_end);
+int aoc_global_match_tc_sharded(const float* q, int HW, const float* S, const float* r2, const int* meta_dev,
+                                int rows_padded, const float* bias, int O, int rank, int world, void* const* areas,
+                                int cap_hw, void* state, void* workspace, size_t ws_bytes, float* out,
+                                cudaStream_t stream);
 int aoc_global_match_finalize_f32(const float* mins, const int* meta, const float* bias, int HW, int O, float* out,
                                   cudaStream_t stream);
 /* cluster level (matching.py:602-637) and k=1 proxy level (matching.py:149-197): out_cluster [HW][O][2], out_proxy [HW][O];

@@ -145,8 +145,10 @@ def test_cfg4_cfg5_vs_oracle_fixture(model, name):
             refs, masks, prev_e, prev_m = [emb], [lab], emb, lab
             for t in range(1, n_pred + 1):
                 np.random.seed(seed if t == 1 else 100 * seed + t)
-                eng.force_proxies = {k: f[k] for k in ("prox_cen", "prox_avg", "prox_ncen", "prox_navg")} \
-                    if (pinned and t == n_pred) else None
+                # pinned: every predicted frame uses the oracle's proxies of that frame (earlier frames reach the
+                # compared one through the decoder memory)
+                eng.force_proxies = {k: f[k][t - 1] for k in ("prox_cen", "prox_avg", "prox_ncen", "prox_navg")} \
+                    if pinned else None
                 probs, emb, mem = model.forward_for_eval(mem, refs, masks, prev_e, prev_m, frames[t:t + 1].to(dev),
                                                          [H, W], gt)
                 if t < n_pred:

@@ -14,7 +14,7 @@ k-means is a DISCRETE step: at these sizes a 1e-6 change of an embedding flips t
 the centroids move by ~1e-2 and the logits by 0.1-0.3 (first attempt of this fixture: float32 vs float64 differed by
 2.9e-1 for exactly that reason) -- a property of the reference algorithm, not of an evaluation.  So the float32 run's
 scipy results (code book + labels per object) are RECORDED and REPLAYED in the float64 run, and the compared frame's
-proxies (centroid, centroid_avg per object) are stored so that the GPU test can pin the engine to the same proxies and
+proxies of EVERY predicted frame (centroid, centroid_avg per object) are stored so that the GPU test can pin the engine to the same proxies and
 compare logits at fp32-rounding level; the engine's own k-means is checked bit for bit on identical inputs elsewhere
 (tests/test_gpu_ops.py::test_kmeans_vs_restatement).
 
@@ -124,12 +124,14 @@ def make(name):
     l64, p64, _ = run(m64.AOCOracle({k: v.double() for k, v in sd.items()}, kmeans_fn=KMReplay(rec.calls)), frames,
                       labels[0], K, seed, n_pred, torch.float64, fed=fed)
     O = K + 1
-    cen, avg = np.zeros((O, 16, 100), np.float32), np.zeros((O, 16, 100), np.float32)
-    ncen, navg = np.zeros(O, np.int32), np.zeros(O, np.int32)
-    for o, pr in enumerate(prox[-1]):                      # the compared frame's proxies
-        if pr is not None:
-            ncen[o], navg[o] = pr[0].shape[0], pr[1].shape[0]
-            cen[o, :ncen[o]] = pr[0].numpy(); avg[o, :navg[o]] = pr[1].numpy()
+    assert len(prox) == n_pred                              # one adaptive_proxies call per predicted frame
+    cen, avg = np.zeros((n_pred, O, 16, 100), np.float32), np.zeros((n_pred, O, 16, 100), np.float32)
+    ncen, navg = np.zeros((n_pred, O), np.int32), np.zeros((n_pred, O), np.int32)
+    for t, frame_prox in enumerate(prox):                  # every predicted frame's proxies (the decoder memory carries
+        for o, pr in enumerate(frame_prox):                # earlier frames' features into the compared frame)
+            if pr is not None:
+                ncen[t, o], navg[t, o] = pr[0].shape[0], pr[1].shape[0]
+                cen[t, o, :ncen[t, o]] = pr[0].numpy(); avg[t, o, :navg[t, o]] = pr[1].numpy()
     noise = (l32.double() - l64).abs().max().item()
     print("%s frame %d: oracle fp32 vs fp64 max|dlogit| %.3e (logit range %.1f); argmax fp32 vs fp64 differs at %d px"
           % (name, n_pred, noise, l64.abs().max().item(), int((p32 != p64).sum())), flush=True)
