@@ -164,8 +164,11 @@ class Stepper:
         return pred
 
 
+SHARD = False       # --bank-shard: every rank runs the same clip with the same numpy stream
+
+
 def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sampler=None):
-    np.random.seed(1000 + (dist.get_rank() if dist else 0))
+    np.random.seed(1000 + (dist.get_rank() if dist and not SHARD else 0))
     st = Stepper(model, frames, first, K_OBJ, device, host_io)
     for _ in range(warmup):
         st.step()
@@ -217,7 +220,8 @@ def kernel_profile(model, frames, first, device, n_frames):
     st = Stepper(model, frames, first, K_OBJ, device, False)   # shapes, just not replayed from the captured graphs
     for _ in range(2):
         st.step()
-    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_kmeans_proxies_f32": [],
+    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_global_match_tc_sharded": [],
+                 "aoc_kmeans_proxies_f32": [],
                  "aoc_affine_stats_nc_f32": [], "aoc_channel_stats_f32": [], "aoc_cond_phi_f32": []}
     km_rows = []
     for _ in range(n_frames):
@@ -239,11 +243,12 @@ def kernel_profile(model, frames, first, device, n_frames):
             fl += 2.0 * N * Ho * Wo * Cout * kh * kw * Cin
             ms += e0.elapsed_time(e1)
         out["conv"] = {"launches": len(conv), "ms": ms, "flop": fl}
-    gm = prof["aoc_global_match_tc"]
+    gm = prof["aoc_global_match_tc"] + prof["aoc_global_match_tc_sharded"]
     if gm:
         fl, ms = 0.0, 0.0
         for e0, e1, a in gm:
-            fl += 2.0 * a[1] * a[5] * 100        # HW x (padded) bank rows x C
+            share = 1.0 / a[9] if len(a) > 12 else 1.0      # sharded: this rank contracts 1 / world of the bank rows
+            fl += 2.0 * a[1] * a[5] * 100 * share           # HW x (padded) bank rows x C
             ms += e0.elapsed_time(e1)
         out["match"] = {"launches": len(gm), "ms": ms, "flop": fl}
     km = prof["aoc_kmeans_proxies_f32"]
@@ -344,6 +349,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=None, help="predicted frames timed for cpu_baseline (per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bank-shard", action="store_true",
+                    help="N > 1: ONE sequence on all N GPUs, the memory bank of the global matching sharded over the ranks "
+                         "(SURVEY 8f-3; strong scaling) instead of one independent clip per GPU")
     args = ap.parse_args()
     global CFG, K_OBJ
     CFG = dict(CONFIGS[args.config])
@@ -399,7 +407,16 @@ def main():
         broadcast_state_dict(model.state_dict(), 0, device)     # the only collective: weights at init
         model._engine = None
     n_frames = 1 + args.warmup + args.steps
-    frames, first, _ = make_workload(rank, n_frames)
+    global SHARD
+    SHARD = bool(args.bank_shard and dist)
+    frames, first, _ = make_workload(0 if SHARD else rank, n_frames)
+    if SHARD:
+        from aocb200.shard import setup_bank_sharding
+        setup_bank_sharding(model.engine(), ((H + 3) // 4) * ((W + 3) // 4))
+        config["workload"] = config["workload"].replace("one independent clip per GPU", "ONE clip on all %d GPUs: every rank "
+                                                        "runs the same frames, the global matching contracts 1/%d of the bank rows "
+                                                        "per rank and exchanges partial minima from inside the kernel over "
+                                                        "NVLink" % (world, world))
 
     # process-level one-time work (lazy workspace allocations, kernel attributes, the first capture of each graph shape
     # through one bank growth) happens in an untimed pre-roll on its own sequence state; the W warm-up steps of the
@@ -414,18 +431,21 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches, clocks = timed_run(model, frames, first, device, args.steps, args.warmup, False, dist, sampler)
     ms_e2e, st2, _, _ = timed_run(model, frames, first, device, args.steps, args.warmup, True, dist)
-    value = world * args.steps / (ms / 1000.0)
-    e2e = world * args.steps / (ms_e2e / 1000.0)
+    seqs = 1 if SHARD else world
+    value = seqs * args.steps / (ms / 1000.0)
+    e2e = seqs * args.steps / (ms_e2e / 1000.0)
 
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "scaling": "strong" if SHARD else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": st2.h2d // args.steps,
                     "d2h_bytes_per_step": st2.d2h // args.steps},
             "gpu_launches": launches, "clocks": clocks}
+    prof_all = kernel_profile(model, frames, first, device, min(6, args.steps)) if SHARD else None   # lockstep: every rank
     if rank == 0:
         pk = peaks()
-        prof = kernel_profile(model, frames, first, device, min(6, args.steps))
+        prof = prof_all if SHARD else kernel_profile(model, frames, first, device, min(6, args.steps))
         step_ms = ms / args.steps
         roofs = {}
         for key, nm, ceil, note, traffic in (

@@ -57,3 +57,55 @@ def test_broadcast_and_gather_world2():
     assert [r["rank"] for r in res] == [0, 1]
     assert all(r["ok"] for r in res), "rank-0 weights did not arrive bit-exactly"
     assert sorted(res[0]["seqs"] + res[1]["seqs"]) == [0, 1, 2, 3, 4]
+
+
+def test_bank_row_block_split_matches_the_library():
+    """the host-side split (shard_row_blocks) is the one the kernel launcher uses (aoc_match_shard_range): contiguous,
+    disjoint, covering, balanced to one 256-row block"""
+    import ctypes
+    from aocb200.lib import lib
+    from aocb200.shard import shard_row_blocks
+    L = lib()
+    for nrb in (0, 1, 2, 7, 101, 2021):
+        for world in (2, 3, 8):
+            parts = [shard_row_blocks(nrb, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == nrb
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+            for r in range(world):
+                a, b = ctypes.c_int(), ctypes.c_int()
+                L.match_shard_range(nrb * 256, r, world, ctypes.byref(a), ctypes.byref(b))
+                assert (a.value, b.value) == parts[r]
+
+
+def _handle_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aocb200.shard import exchange_handles
+        mine = bytes([rank]) * 64                                # stand-in for a 64-byte CUDA IPC handle
+        got = exchange_handles(mine)
+        if rank == 0:
+            q.put(got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ipc_handle_exchange_world2():
+    """the init-time exchange of the exchange areas' IPC handles (the only host collective of the bank-sharded mode)"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_handle_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [bytes([0]) * 64, bytes([1]) * 64]
