@@ -49,13 +49,18 @@ constexpr int C2_WRB = 128;                             // rows per block of the
 // bytes of one (row block, stage) weight chunk: 128 rows x 16 channels x {hi, lo}: 3xTF32 16384, split-fp16 8192
 __host__ __device__ constexpr uint32_t c2_wchunk(bool f16) { return C2_WRB * C2_KC * (f16 ? 2u : 4u) * 2u; }
 constexpr int C2_MAX_AFFINE_C = 1024;
+constexpr int C2_MAX_KSPLIT = 8;                        // split-K slices per output tile
 // setmaxnreg targets.  The CTA's registers are fixed at launch (20 warps x 96); an increase can only take what decreases
 // of the same CTA have released, so 8 x 80 (transform) + 8 x 136 (drain) + 4 x 40 (TMA / MMA issue) <= 20 x 96.
-constexpr int C2_REGS_XFORM = 80;
-constexpr int C2_REGS_DRAIN = 136;
-constexpr int C2_REGS_MISC = 40;
-static_assert(8 * C2_REGS_XFORM + 8 * C2_REGS_DRAIN + 4 * C2_REGS_MISC <= 20 * 96, "register budget of the CTA");
-constexpr int C2_THREADS = 672;                         // 8 transform + 8 drain + 2 producer + up to 3 issuer warps
+constexpr int C2_NS = 2;                                // transform sets (four warps each); 3 measured: no gain, the large layers are then bound by L2 -> SM bandwidth
+constexpr int C2_XW = 4 * C2_NS;                        // transform warps = first drain warp
+constexpr int C2_XT = 32 * C2_XW;                       // transform threads = first drain thread
+constexpr int C2_LAUNCH_REGS = C2_NS == 2 ? 96 : 80;    // what ptxas gives a thread under __launch_bounds__(32 * (C2_XW + 12), 1)
+constexpr int C2_REGS_XFORM = C2_NS == 2 ? 80 : 64;
+constexpr int C2_REGS_DRAIN = C2_NS == 2 ? 136 : 128;
+constexpr int C2_REGS_MISC = C2_NS == 2 ? 40 : 32;
+static_assert(C2_XW * C2_REGS_XFORM + 8 * C2_REGS_DRAIN + 4 * C2_REGS_MISC <= (C2_XW + 12) * C2_LAUNCH_REGS,
+              "setmaxnreg.inc can only take what the CTA's own warps released: an over-subscribed budget blocks forever");
 
 struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
@@ -115,7 +120,7 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
 // ~385 cycles per stage, hence one full barrier per PAIR of stages for both operands and two stages per iteration.
 template <int TN, bool F16>
 struct C2Cfg {
-    static constexpr int NR = 6;                             // raw activation ring depth (128 pixels x 32 channels each)
+    static constexpr int NR = C2_NS == 2 ? 6 : 7;            // raw activation ring depth (128 pixels x 32 channels each)
     // operand ring (activation half in TMEM, 32 columns per stage; weight half in shared memory): a weight chunk is
     // requested when the stage it replaces retires and needs an L2 round trip (~1.5k cycles) to land, so the period of
     // a stage cannot drop below (round trip + MMA time) / depth: 8 stages where TMEM has room (TN = 64), else 4
@@ -135,7 +140,7 @@ struct C2Cfg {
     // accumulator per term (TN = 64: a stage is only 192 tensor cycles, the ~75 cycles per tcgen05 instruction of an
     // issuing thread are the limit -- so the 6 MMAs of a stage are spread over three threads)
     static constexpr int NCI = 1;   // (a third issuer for TN = 64 was measured: no gain once the weight latency is the limit)
-    static constexpr int THREADS = (8 + 8 + 2 + 1 + NCI) * 32;
+    static constexpr int THREADS = (C2_XW + 8 + 2 + 1 + NCI) * 32;
     static constexpr uint32_t A_TMEM_COL = (2 + NCB * NCI) * TN;   // ring of C2_NO stages x 32 columns behind the accumulators
 };
 
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     // and run its prologue (barrier init, TMEM allocation, descriptor fetch) under our tail; every role that touches
     // global memory first executes griddepcontrol.wait (= the previous grid has completed and its writes are visible).
     asm volatile("griddepcontrol.launch_dependents;");
-    if (warp == 17 && lane == 0) {
+    if (warp == C2_XW + 9 && lane == 0) {
         for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
         for (int q = 0; q < C2_NO / 2; ++q) { mbar_init(OP_FULL(q), 10); mbar_init(OP_EMPTY(q), 1 + NCI); }
         for (int b = 0; b < 2; ++b) {
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         }
         fence_barrier_init();
     }
-    if (warp == 18) {
+    if (warp == C2_XW + 10) {
         tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
         tmem_relinquish();
     }
@@ -235,9 +240,9 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp < 18) asm volatile("griddepcontrol.wait;" ::: "memory");       // transform, drain, TMA producers
+    if (warp < C2_XW + 10) asm volatile("griddepcontrol.wait;" ::: "memory");       // transform, drain, TMA producers
 
-    if (warp < 8) {
+    if (warp < C2_XW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
         // ===== transform warps: two sets of four (set g owns the operand stages with an even / odd running index, so a
         // set's per-stage instruction stream -- ~550 cycles -- has two stage-times to complete); thread <-> pixel row <->
@@ -253,7 +258,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         int sr = 0, so = 0;
         uint32_t pr = 0, po = 0;
         int tab_n = -1;
-        int bi = 0;                                                          // running raw-box index (parity = owner set)
+        int bi = 0;                                                          // owner set of the next raw box (running index mod C2_NS)
+        int last_owner = -1;                                                 // owner of the most recent box
         int pend = -1;                                                       // operand slot stored but not yet published
         float amax = 0.f;                                                    // largest |operand| this thread converted to fp16
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
@@ -261,14 +267,14 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
             if (affine && tl.n != tab_n) {
                 // per-(sample, channel) coefficient table of this image; only the transform warps touch it
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
                 const int cpad = p.ncc * C2_KC;
-                for (int c = threadIdx.x; c < cpad; c += 256) {
+                for (int c = threadIdx.x; c < cpad; c += C2_XT) {
                     const bool ok = c < p.Cin;
                     tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)tl.n * p.Cin + c) : 1.f) : 0.f;
                     tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)tl.n * p.Cin + c) : 0.f;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
                 tab_n = tl.n;
             }
             int tap = tl.tap0, cc = tl.cc0;
@@ -281,9 +287,9 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             // A set owns whole raw boxes (32 channels = two operand stages, one for an odd tail), alternating with the
             // other set; the box's RAW_FULL / RAW_EMPTY barriers are touched by the owner only (RAW_EMPTY counts its four
             // warps), so a set spends a handful of counter updates on a box it does not own.
-            for (int rb = tl.r0; rb < tl.r1; ++rb, ++bi) {
+            for (int rb = tl.r0; rb < tl.r1; ++rb) {
                 const int nst = (cc + 1 < p.ncc) ? 2 : 1;
-                if ((bi & 1) == g) {
+                if (bi == g) {
                     mbar_wait(RAW_FULL(sr), pr);
                     const uint32_t rawb = raw0 + sr * C2_RAW_BYTES + src_row;
                     int so_s = so;
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
 #pragma unroll 1
                     for (int hs = 0; hs < nst; ++hs) {
                         const int ccs = cc + hs;
-                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(1, tap * p.ncc + ccs);
+                        if (threadIdx.x == 0 || threadIdx.x == 128 || threadIdx.x == 256) C2_TRACE(1, tap * p.ncc + ccs);
                         float v[16];
                         const uint32_t c8 = (uint32_t)hs * 4u;
                         if (C2_DBG(8)) {
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                                 o[(e >> 3) * 16 + 8 + (e & 7)] = l;
                             }
                         }
-                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(2, tap * p.ncc + ccs);
+                        if (threadIdx.x == 0 || threadIdx.x == 128 || threadIdx.x == 256) C2_TRACE(2, tap * p.ncc + ccs);
                         // the tensor-memory store of the set's previous stage completes under this stage's ALU work: it
                         // is waited for and published only now (the MMA side runs stages behind, nothing waits on it)
                         if (pend >= 0) {
@@ -369,12 +375,12 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         }
                         // the slot's pair was released as a whole: one wait per pair the box touches
                         if (hs == 0 || (so_s & 1) == 0) mbar_wait(OP_EMPTY(so_s >> 1), po_s ^ 1u);
-                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(3, tap * p.ncc + ccs);
+                        if (threadIdx.x == 0 || threadIdx.x == 128 || threadIdx.x == 256) C2_TRACE(3, tap * p.ncc + ccs);
                         tc_fence_after();
                         if (F16) tmem_st16(a_lane + (uint32_t)(so_s * Cfg::A_COLS), o);
                         else     tmem_st32(a_lane + (uint32_t)(so_s * Cfg::A_COLS), o);
                         pend = so_s;
-                        if (threadIdx.x == 0 || threadIdx.x == 128) C2_TRACE(4, tap * p.ncc + ccs);
+                        if (threadIdx.x == 0 || threadIdx.x == 128 || threadIdx.x == 256) C2_TRACE(4, tap * p.ncc + ccs);
                         if (++so_s == C2_NO) { so_s = 0; po_s ^= 1u; }
                     }
                     // the box's last stage is published before the set moves on (deferred to the set's next box, two
@@ -385,6 +391,8 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     if (lane == 0) { mbar_arrive(OP_FULL(pend >> 1)); mbar_arrive(RAW_EMPTY(sr)); }
                     pend = -1;
                 }
+                last_owner = bi;
+                if (++bi == C2_NS) bi = 0;
                 if (++sr == C2_NR) { sr = 0; pr ^= 1u; }
                 so += nst;
                 if (so >= C2_NO) { so -= C2_NO; po ^= 1u; }
@@ -401,17 +409,17 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         // an odd number of stages leaves the last pair half filled: the issuers wait for whole pairs, so one set (and the
         // weight producer) supply the missing stage's arrivals
         // (the set that owned the last box: its real arrival for that pair is already in, so the phase is the right one)
-        if ((so & 1) && ((bi - 1) & 1) == g && lane == 0) mbar_arrive(OP_FULL(so >> 1));
+        if ((so & 1) && last_owner == g && lane == 0) mbar_arrive(OP_FULL(so >> 1));
         // cvt.rn.satfinite clamps at 65504: a clamped operand means a wrong result, so it is reported (sticky word; the
         // host re-runs the frame with 3xTF32 operands, which have the fp32 exponent range)
         if (F16 && p.overflow && amax >= 6.0e4f) *p.overflow = 1;
-    } else if (warp < 16) {
+    } else if (warp < C2_XW + 8) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
         // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
         // tcgen05.ld per thread; the producer / issuer warpgroup gives its share back)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REGS_DRAIN));
         constexpr int NC = TN / 2;
-        const int dwp = warp - 8;
+        const int dwp = warp - C2_XW;
         const int q = dwp & 3, half = dwp >> 2;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NC);
         const uint32_t stg = smem_u32(smem + Cfg::STG_OFF) + (uint32_t)(dwp * 4096);
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             for (int ch = 0; ch < nchunks; ++ch) {
                 if (b == 0) { mbar_wait(MAIN_FULL(0), ph0); ph0 ^= 1u; }
                 else        { mbar_wait(MAIN_FULL(1), ph1); ph1 ^= 1u; }
-                if (threadIdx.x == 256) C2_TRACE(11, tl.it0 + ch * p.chunk);
+                if (threadIdx.x == C2_XT) C2_TRACE(11, tl.it0 + ch * p.chunk);
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < NC; c0 += 32) {
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(MAIN_EMPTY(b));
-                if (threadIdx.x == 256) C2_TRACE(12, tl.it0 + ch * p.chunk);
+                if (threadIdx.x == C2_XT) C2_TRACE(12, tl.it0 + ch * p.chunk);
                 b ^= 1;
             }
             // the correction terms are issued by their own warp: wait for its end-of-tile commit
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 int* cnt = p.ws_cnt + t / p.ksplit;
                 __threadfence();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (threadIdx.x == 256) {
+                if (threadIdx.x == C2_XT) {
                     atomicAdd(cnt, 1);
                     int v;
                     do {
@@ -579,16 +587,27 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     const size_t Mtot = (size_t)p.N * p.Ho * p.Wo;
                     constexpr int C4 = TN / 4;
                     const int m_lo = C2_BM * tl.ks / p.ksplit, m_hi = C2_BM * (tl.ks + 1) / p.ksplit;
-                    for (int i = m_lo * C4 + (threadIdx.x - 256); i < m_hi * C4; i += 256) {
+                    for (int i = m_lo * C4 + (threadIdx.x - C2_XT); i < m_hi * C4; i += 256) {
                         const int m = i / C4, c = (i - m * C4) * 4;
                         const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
                         const int co = tl.n0 + c;
                         if (ho >= p.Ho || wo >= p.Wo || co >= p.Cout) continue;   // (Cout % 4 == 0 on this path)
                         const size_t pix = ((size_t)tl.n * p.Ho + ho) * p.Wo + wo;
-                        float4 a = __ldcg(reinterpret_cast<const float4*>(p.ws + pix * p.Cout + co));
-                        for (int k = 1; k < p.ksplit; ++k) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)k * Mtot + pix) * p.Cout + co));
-                            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+                        // every slice's partial sum is requested before the first add (one L2 round trip instead of
+                        // ksplit dependent ones); the adds keep the slice order
+                        constexpr int NF = 5;                            // slices in flight (the 31x54 backbone maps split 5 ways)
+                        float4 v[NF];
+#pragma unroll
+                        for (int k = 0; k < NF; ++k)
+                            if (k < p.ksplit)
+                                v[k] = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)k * Mtot + pix) * p.Cout + co));
+                        float4 a = v[0];
+#pragma unroll
+                        for (int k = 1; k < NF; ++k)
+                            if (k < p.ksplit) { a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w; }
+                        for (int k = NF; k < p.ksplit; ++k) {
+                            const float4 u = __ldcg(reinterpret_cast<const float4*>(p.ws + ((size_t)k * Mtot + pix) * p.Cout + co));
+                            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
                         }
                         if (p.bias) { const float4 b = ldg4(p.bias + co); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
                         if (p.res) {
@@ -600,12 +619,12 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     }
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");          // every thread of this slice has read the partial sums
-                if (threadIdx.x == 256 && atomicAdd(cnt, 1) == 2 * p.ksplit - 1) *cnt = 0;
+                if (threadIdx.x == C2_XT && atomicAdd(cnt, 1) == 2 * p.ksplit - 1) *cnt = 0;
             }
             if (!SK && p.tile_stats) {
                 // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels
                 asm volatile("bar.sync 2, 256;" ::: "memory");
-                const int i = threadIdx.x - 256;                                 // 0..255 over [stat][TN] (TN <= 128)
+                const int i = threadIdx.x - C2_XT;                              // 0..255 over [stat][TN] (TN <= 128)
                 if (i < 2 * TN) {
                     const int stat = i / TN, ch = i - stat * TN;
                     const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
@@ -616,7 +635,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
-    } else if (warp == 16) {
+    } else if (warp == C2_XW + 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         if (lane == 0) {
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 }
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == C2_XW + 9) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         if (lane == 0) {
             // ===== weight TMA producer: chunk (row block, stage) = [ks0: hi | lo][ks1: hi | lo], 4096 B blocks =====
@@ -680,7 +699,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             }
             if (sb_ & 1) mbar_arrive(OP_FULL(sb_ >> 1));          // odd stage count: complete the last pair (see transform)
         }
-    } else if (warp == 18) {
+    } else if (warp == C2_XW + 10) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== MAIN issuer (hi*hi): the whole warp runs the (warp-uniform) loop, one elected lane issues =====
         const uint32_t idesc = F16 ? idesc_f16(C2_BM, TN) : idesc_tf32(C2_BM, TN);
@@ -742,10 +761,10 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 if (so == C2_NO) { so = 0; po ^= 1u; }
             }
         }
-    } else if (warp >= 19 && warp < 19 + NCI) {
+    } else if (warp >= C2_XW + 11 && warp < C2_XW + 11 + NCI) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_MISC));
         // ===== CORR issuer(s): lo*hi + hi*lo into CORR (one warp), or one term and one accumulator per warp =====
-        const int ci = warp - 19;
+        const int ci = warp - (C2_XW + 11);
         const uint32_t idesc = F16 ? idesc_f16(C2_BM, TN) : idesc_tf32(C2_BM, TN);
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, cb = 0;
@@ -804,7 +823,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 18) {
+    if (warp == C2_XW + 10) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
@@ -890,7 +909,6 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-constexpr int C2_MAX_KSPLIT = 8;
 constexpr size_t C2_WS_HEADER = 4096;   // split-K arrival counters (one int per output tile) in front of the partial sums
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
 int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels

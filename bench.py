@@ -199,10 +199,11 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
     gc.enable()
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
-    if host_io:        # diagnostic (stderr): host wall time per step of the end-to-end run -- a single stalled step shows here
+    if os.environ.get("RANK", "0") == "0":   # diagnostic (stderr): host wall time per step -- a single stalled step shows here
         ws = sorted(walls)
-        print("e2e host wall per step: median %.2f ms, max %.2f ms (step %d), sum %.1f ms; device %.1f ms"
-              % (1e3 * ws[len(ws) // 2], 1e3 * ws[-1], walls.index(ws[-1]), 1e3 * sum(walls), ms), file=sys.stderr)
+        print("%s host wall per step: median %.2f ms, max %.2f ms (step %d), sum %.1f ms; device %.1f ms; all: %s"
+              % ("e2e" if host_io else "resident", 1e3 * ws[len(ws) // 2], 1e3 * ws[-1], walls.index(ws[-1]),
+                 1e3 * sum(walls), ms, " ".join("%.1f" % (1e3 * w) for w in walls)), file=sys.stderr)
     if dist:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

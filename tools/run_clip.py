@@ -50,6 +50,9 @@ def main():
     print("host issue time %.3f ms/frame (python + launches, GPU running behind)" % (1e3 * t_issue / args.frames))
     torch.cuda.profiler.stop()
     print("frames %d  %.3f ms/frame (%dx%d, K=%d)" % (args.frames, e0.elapsed_time(e1) / args.frames, H, W, args.K))
+    bk = model.engine().bank
+    print("bank at the profiled frame: %d frame(s) of %d pixels, %d object-sorted rows (padded), per-object pixel counts %s"
+          % (bk.n, bk.hw, bk.index["rows"], bk.index["counts"]))
 
 
 if __name__ == "__main__":
