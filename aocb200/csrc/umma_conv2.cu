@@ -52,7 +52,12 @@ constexpr int C2_MAX_AFFINE_C = 1024;
 constexpr int C2_MAX_KSPLIT = 8;                        // split-K slices per output tile
 // setmaxnreg targets.  The CTA's registers are fixed at launch (20 warps x 96); an increase can only take what decreases
 // of the same CTA have released, so 8 x 80 (transform) + 8 x 136 (drain) + 4 x 40 (TMA / MMA issue) <= 20 x 96.
-constexpr int C2_NS = 2;                                // transform sets (four warps each); 3 measured: no gain, the large layers are then bound by L2 -> SM bandwidth
+#ifndef AOC_CONV_NS
+#define AOC_CONV_NS 2
+#endif
+// transform sets (four warps each).  3 sets measured (tooling build -DAOC_CONV_NS=3): no gain on the large layers, which
+// are then bound by L2 -> SM bandwidth (16 KB of weights + raw patch per stage and SM), see DESIGN section 4
+constexpr int C2_NS = AOC_CONV_NS;
 constexpr int C2_XW = 4 * C2_NS;                        // transform warps = first drain warp
 constexpr int C2_XT = 32 * C2_XW;                       // transform threads = first drain thread
 constexpr int C2_LAUNCH_REGS = C2_NS == 2 ? 96 : 80;    // what ptxas gives a thread under __launch_bounds__(32 * (C2_XW + 12), 1)
