@@ -107,8 +107,11 @@ def test_480p_k5_vs_oracle(model, state_dict):
 # observed x 1.5 (B200, round 2): see the [parity] lines these tests print
 CFG_BOUNDS = {
     # name: (|engine - fp64| with pinned proxies, |engine - oracle fp32| with pinned proxies, argmax pixels differing)
-    "cfg4_720p_k10": (2.0e-2, 2.5e-2, 400),
-    "cfg5_1080p_k5_bank3": (2.0e-2, 2.5e-2, 400),
+    # observed: cfg4 1.57e-2 / 1.63e-2 / 236 px of 923 601 (the oracle's own fp32 run: 9.8e-3 from float64)
+    "cfg4_720p_k10": (2.4e-2, 2.5e-2, 360),
+    # observed: cfg5 1.03e-2 / 1.11e-2 / 558 px of 2 061 233 (the oracle's own fp32 run: 7.4e-3 from float64, its argmax differs
+    # from the float64 run's at 467 px)
+    "cfg5_1080p_k5_bank3": (1.6e-2, 1.7e-2, 840),
 }
 
 
