@@ -84,7 +84,9 @@ struct Conv2P {
 };
 
 #ifdef AOC_CONV_TRACE   // tooling build only (tools/conv_trace.py): keeps the production kernel's code small
-#define C2_TRACE(ev, st) do { if (p.trace && blockIdx.x == 0 && (st) < 256) p.trace[(ev) * 256 + (st)] = clock64(); } while (0)
+// stage index of an event = running stage count of CTA 0 (tile ordinal x stages per tile + stage): short-K layers show several tiles
+#define C2_TRACE(ev, st) do { const int st_ = (t - (int)blockIdx.x) / (int)gridDim.x * nIt + (st); \
+                              if (p.trace && blockIdx.x == 0 && st_ < 256) p.trace[(ev) * 256 + st_] = clock64(); } while (0)
 // ablation switches of the tooling build (aoc_set_option("conv_dbg", bits); results are garbage, the timing is the point):
 // 1 no weight copies (the barrier is completed by a plain arrive), 2 no activation TMA, 4 no correction MMAs,
 // 8 no transform arithmetic (zeros are stored), 16 no main MMAs
@@ -108,6 +110,17 @@ __device__ __forceinline__ void ffma2(float& x0, float& x1, float a0, float a1, 
     asm("{\n\t.reg .b64 x, a, b;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\t"
         "fma.rn.f32x2 x, x, a, b;\n\tmov.b64 {%0, %1}, x;\n\t}"
         : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// (d0, d1) += (a0, a1) and (d0, d1) += (a0 * a0, a1 * a1): the per-channel statistics of the epilogue
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+    asm("{\n\t.reg .b64 d, a;\n\tmov.b64 d, {%0, %1};\n\tmov.b64 a, {%2, %3};\n\t"
+        "add.rn.f32x2 d, d, a;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void fsqacc2(float& d0, float& d1, float a0, float a1) {
+    asm("{\n\t.reg .b64 d, a;\n\tmov.b64 d, {%0, %1};\n\tmov.b64 a, {%2, %3};\n\t"
+        "fma.rn.f32x2 d, a, a, d;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 __device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
     asm("{\n\t.reg .b64 x, c;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 c, {%2, %2};\n\t"
@@ -135,8 +148,7 @@ struct C2Cfg {
     static constexpr uint32_t RAW_OFF = 0;
     static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + NO * B_BYTES;
-    static constexpr uint32_t STAT_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;    // [4 quadrants][2 stats][TN] floats
-    static constexpr uint32_t STG_OFF = STAT_OFF + 4 * 2 * TN * 4;             // epilogue staging: 8 warps x 32 rows x 128 B
+    static constexpr uint32_t STG_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;     // epilogue staging: 8 warps x 32 rows x 128 B
     static constexpr uint32_t BAR_OFF = STG_OFF + 8 * 4096;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
@@ -472,12 +484,16 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
+            if (threadIdx.x == C2_XT) C2_TRACE(13, tl.it0);
             if (NCB == 2) cb ^= 1;
             // ---- epilogue.  The accumulators sit one pixel row per thread; stored that way every warp store would touch 32
             // different lines (and the residual loads likewise).  Each warp therefore transposes 32 pixels x 32 channels
             // through a private, XOR-swizzled 4 KB staging block: on the way back 8 lanes cover the 128 contiguous bytes
             // of one pixel, so residual loads and output stores are whole 128-byte lines, the bias is one float4 per lane,
             // and the GroupNorm / GCT statistics need two shuffles per value instead of a 32-lane butterfly.
+            // The 32-channel chunks of a warp run through ONE copy of this code (rolled loop, the upper chunk rotated into
+            // acc[0..31]): the unrolled version was 3 000 instructions per kernel, and on the short-K layers -- where the
+            // epilogue is the critical path -- a third of the drain warps' stalls were instruction-cache misses.
             const int cbase = tl.n0 + half * NC;
             const bool partial = SK;                                 // split-K: raw partial sums of this K slice to `ws`
             float* const ybase = partial ? p.ws + (size_t)tl.ks * ((size_t)p.N * p.Ho * p.Wo) * p.Cout : p.y;
@@ -486,21 +502,27 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             const float* const resb = partial ? nullptr : p.res;
             const bool relu = !partial && p.relu;
             const int r_sub = lane >> 3, ch4 = lane & 7;
-            float* st = reinterpret_cast<float*>(smem + Cfg::STAT_OFF);      // [q][stat][TN]
-            int pixi[8];                                             // output pixel of row i * 4 + r_sub (-1: outside)
+            // statistics row of this warp: (pixel tile, 32-pixel quadrant) -- no cross-warp step, no block barrier
+            float* const strow = (!SK && p.tile_stats) ? p.tile_stats + (size_t)((t / p.tiles_n) * 4 + q) * 2 * p.Cout : nullptr;
+            int pixi[8], rowoff[8];                                  // output pixel of row i * 4 + r_sub (-1: outside), its offset in y
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int m = q * 32 + i * 4 + r_sub;
                 const int ho = tl.ho0 + (m >> p.tw_log2), wo = tl.wo0 + (m & tw_mask);
                 pixi[i] = (ho < p.Ho && wo < p.Wo) ? (tl.n * p.Ho + ho) * p.Wo + wo : -1;
+                rowoff[i] = pixi[i] * ldo;                           // (the launcher checks that the output fits 2^31 elements)
             }
-#pragma unroll
+#pragma unroll 1
             for (int c0 = 0; c0 < NC; c0 += 32) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4))),
-                                 "f"(acc[c0 + 4 * j]), "f"(acc[c0 + 4 * j + 1]), "f"(acc[c0 + 4 * j + 2]), "f"(acc[c0 + 4 * j + 3])
+                                 "f"(acc[4 * j]), "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
                                  : "memory");
+                if (NC > 32) {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[e] = acc[(32 + e) % NC];
+                }
                 __syncwarp();
                 const int co = cbase + c0 + ch4 * 4;
                 const bool vec = p.vec_out && co + 3 < p.Cout;
@@ -511,47 +533,73 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                         if (co + e < p.Cout) b4[e] = __ldg(bias + co + e);
                 }
                 float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                if (vec) {
+                    // four rows at a time: their staging reads (and residual lines) are requested before the first use;
+                    // bias / residual / ReLU / statistics cost instructions only where the layer has them (warp-uniform
+                    // branches), the statistics are packed f32x2 operations
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + r_sub;
-                    const bool valid = pixi[i] >= 0 && co < p.Cout;
-                    float o[4];
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                                 : "r"(stg + (uint32_t)(r * 128 + ((ch4 ^ (r & 7)) << 4))));
-                    if (valid) {
-                        const size_t pix = (size_t)pixi[i];
-                        float* dst = ybase + pix * ldo + co;
-                        if (vec) {
-                            if (resb) {
-                                const float4 r4 = ldg4(resb + pix * p.ldres + co);
-                                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-                            }
+                    for (int h = 0; h < 2; ++h) {
+                        float o[4][4];
+                        float4 r4[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                o[e] += b4[e];
-                                if (relu) o[e] = fmaxf(o[e], 0.f);
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = h * 4 + k, r = i * 4 + r_sub;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(o[k][0]), "=f"(o[k][1]), "=f"(o[k][2]), "=f"(o[k][3])
+                                         : "r"(stg + (uint32_t)(r * 128 + ((ch4 ^ (r & 7)) << 4))));
+                            if (resb) r4[k] = pixi[i] >= 0 ? ldg4(resb + (size_t)pixi[i] * p.ldres + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = h * 4 + k;
+                            if (pixi[i] >= 0) {
+                                if (resb) { o[k][0] += r4[k].x; o[k][1] += r4[k].y; o[k][2] += r4[k].z; o[k][3] += r4[k].w; }
+                                if (bias) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) o[k][e] += b4[e];
+                                }
+                                if (relu) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) o[k][e] = fmaxf(o[k][e], 0.f);
+                                }
+                                if (strow) {
+                                    fadd2(s1[0], s1[1], o[k][0], o[k][1]);
+                                    fadd2(s1[2], s1[3], o[k][2], o[k][3]);
+                                    fsqacc2(s2[0], s2[1], o[k][0], o[k][1]);
+                                    fsqacc2(s2[2], s2[3], o[k][2], o[k][3]);
+                                }
+                                *reinterpret_cast<float4*>(ybase + (size_t)(rowoff[i] + co)) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
                             }
-                            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                        } else {
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {                    // ragged channel count / unaligned rows: scalar accesses
+                        const int r = i * 4 + r_sub;
+                        float o[4];
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                                     : "r"(stg + (uint32_t)(r * 128 + ((ch4 ^ (r & 7)) << 4))));
+                        int pix = -1;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pix = (k == i) ? pixi[k] : pix;
+                        if (pix >= 0) {
+                            float* dst = ybase + (size_t)pix * ldo + co;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 if (co + e < p.Cout) {
-                                    if (resb) o[e] += __ldg(resb + pix * p.ldres + co + e);
+                                    if (resb) o[e] += __ldg(resb + (size_t)pix * p.ldres + co + e);
                                     o[e] += b4[e];
                                     if (relu) o[e] = fmaxf(o[e], 0.f);
                                     dst[e] = o[e];
-                                } else {
-                                    o[e] = 0.f;
+                                    s1[e] += o[e]; s2[e] = fmaf(o[e], o[e], s2[e]);
                                 }
                             }
                         }
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { s1[e] += o[e]; s2[e] = fmaf(o[e], o[e], s2[e]); }
                     }
                 }
                 __syncwarp();                                        // the staging block is rewritten by the next chunk
-                if (!SK && p.tile_stats) {
+                if (strow) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
@@ -561,13 +609,12 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                     }
                     if (lane < 8) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            st[(q * 2 + 0) * TN + half * NC + c0 + ch4 * 4 + e] = s1[e];
-                            st[(q * 2 + 1) * TN + half * NC + c0 + ch4 * 4 + e] = s2[e];
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (co + e < p.Cout) { strow[co + e] = s1[e]; strow[p.Cout + co + e] = s2[e]; }
                     }
                 }
             }
+            if (threadIdx.x == C2_XT) C2_TRACE(14, tl.it0);
             if (SK) {
                 // ---- split-K finish, fused (the separate finish kernel -- 65 launches per frame on the 31x54 backbone maps --
                 // is gone).  Every K slice of a tile runs on its own CTA at the same time (the launcher splits only when
@@ -625,19 +672,6 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");          // every thread of this slice has read the partial sums
                 if (threadIdx.x == C2_XT && atomicAdd(cnt, 1) == 2 * p.ksplit - 1) *cnt = 0;
-            }
-            if (!SK && p.tile_stats) {
-                // fused GroupNorm / GCT statistics: per-channel sum and sum of squares of this tile's 128 pixels
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                const int i = threadIdx.x - C2_XT;                              // 0..255 over [stat][TN] (TN <= 128)
-                if (i < 2 * TN) {
-                    const int stat = i / TN, ch = i - stat * TN;
-                    const float t4 = ((st[(0 * 2 + stat) * TN + ch] + st[(1 * 2 + stat) * TN + ch]) +
-                                      st[(2 * 2 + stat) * TN + ch]) + st[(3 * 2 + stat) * TN + ch];
-                    const int mt = t / p.tiles_n;
-                    if (tl.n0 + ch < p.Cout) p.tile_stats[((size_t)mt * 2 + stat) * p.Cout + tl.n0 + ch] = t4;
-                }
-                asm volatile("bar.sync 2, 256;" ::: "memory");
             }
         }
     } else if (warp == C2_XW + 8) {
@@ -1028,7 +1062,7 @@ extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
     if (Ho <= 0 || Wo <= 0) return 0;
-    return cdiv(Wo, 1 << l2) * cdiv(Ho, C2_BM >> l2);
+    return 4 * cdiv(Wo, 1 << l2) * cdiv(Ho, C2_BM >> l2);     // one statistics row per 32-pixel quadrant of a 128-pixel tile
 }
 
 extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, const float* residual,
@@ -1052,6 +1086,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     int gH, gW, Ho, Wo, best_l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &best_l2);
     AOC_CHECK_ARG(Ho > 0 && Wo > 0, "empty output");
+    AOC_CHECK_ARG((long long)N * Ho * Wo * (ldy > Cout ? ldy : Cout) < (1ll << 31), "output larger than 2^31 elements");
     Conv2P p;
     p.w = (const uint8_t*)w_packed; p.bias = bias; p.res = residual; p.in_a = in_a; p.in_b = in_b; p.y = y;
     p.tile_stats = tile_stats;

@@ -91,7 +91,8 @@ int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const float* bias, 
  * are arrival counters that must be ZERO when the caller first hands the buffer over; every launch leaves them zero
  * again (the K slice that arrives last at a tile adds the slices in index order, finishes the tile and resets it). */
 size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil);
-/* tile_stats (optional): [N * aoc_conv_tiles_per_image(...)][2][Cout] floats receiving, per 128-pixel output tile, the
+/* tile_stats (optional): [N * aoc_conv_tiles_per_image(...)][2][Cout] floats receiving, per statistics row (= a 32-pixel
+ * quadrant of a 128-pixel output tile: what one epilogue warp stores; aoc_conv_tiles_per_image counts these rows), the
  * per-channel sum and sum of squares of the stored output -- the GroupNorm / GCT statistics of the next layer come
  * out of the convolution epilogue instead of a second pass over the tensor (aoc_tile_stats_reduce_f32 folds them into
  * the [N][2][C] double layout of aoc_channel_stats_f32). */
