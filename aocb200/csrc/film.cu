@@ -40,37 +40,85 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// k-th largest (k is 1-based) of vals[n, 0..L) per n: 4-pass MSB radix select, one block per n.
-__global__ void __launch_bounds__(1024) kth_largest_kernel(const float* __restrict__ vals, int L, int k,
-                                                            float* __restrict__ out) {
-    __shared__ unsigned hist[256];
+// k-th largest (k is 1-based) of vals[n, 0..L) per n: 4-pass MSB radix select, one block per n (exact: the threshold is
+// compared with `>` against every phi value, conditioning_layer.py:34-37).  The row is read from global memory ONCE, as
+// order-preserving unsigned keys, into shared memory (100 KB for a 121 x 213 map); every pass then histograms the keys
+// that still match the selected prefix into per-warp histograms -- lanes of a warp that hit the same bin are combined
+// with match.any first (phi values share their exponent byte: the first pass would otherwise be a 32-way conflict on one
+// counter) -- and one warp finds the bin that holds the k-th key with a shuffle scan.  Round 1's version re-read the row
+// from L2 in every pass and funnelled all 1024 threads into one histogram: 32-38 us per call, now bounded by ~25
+// shared-memory iterations per pass.
+constexpr int KTH_THREADS = 1024;
+constexpr int KTH_WARPS = KTH_THREADS / 32;
+__global__ void __launch_bounds__(KTH_THREADS) kth_largest_kernel(const float* __restrict__ vals, int L, int k,
+                                                                   float* __restrict__ out, int keys_in_smem) {
+    extern __shared__ unsigned kth_smem[];
+    unsigned* whist = kth_smem;                                  // [KTH_WARPS][256]
+    unsigned* hist = whist + KTH_WARPS * 256;                    // [256]
+    unsigned* keys = hist + 256;                                 // [L] when keys_in_smem
     __shared__ unsigned s_prefix, s_k;
     const float* v = vals + (size_t)blockIdx.x * L;
-    if (threadIdx.x == 0) { s_prefix = 0u; s_k = (unsigned)k; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_prefix = 0u; s_k = (unsigned)k; }
+    if (keys_in_smem)
+        for (int i = tid; i < L; i += KTH_THREADS) keys[i] = f2ord(__ldg(v + i));
+    const int Lr = (L + KTH_THREADS - 1) / KTH_THREADS * KTH_THREADS;
     for (int pass = 0; pass < 4; ++pass) {
-        int shift = 24 - 8 * pass;
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < KTH_WARPS * 256; i += KTH_THREADS) whist[i] = 0u;
         __syncthreads();
-        unsigned prefix = s_prefix;
-        unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = threadIdx.x; i < L; i += blockDim.x) {
-            unsigned u = f2ord(__ldg(v + i));
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        const unsigned prefix = s_prefix;
+        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < Lr; i += KTH_THREADS) {            // warp-uniform trip count (ballot / match below)
+            unsigned u = 0u;
+            bool in = false;
+            if (i < L) {
+                u = keys_in_smem ? keys[i] : f2ord(__ldg(v + i));
+                in = (u & mask) == prefix;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned bin = (u >> shift) & 255u;
+                const unsigned same = __match_any_sync(act, bin);
+                if (lane == __ffs(same) - 1) atomicAdd(&whist[warp * 256 + bin], (unsigned)__popc(same));
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned need = s_k, run = 0u;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (run + hist[b] >= need) break;
-                run += hist[b];
+        if (tid < 256) {
+            unsigned t = 0u;
+#pragma unroll 8
+            for (int w = 0; w < KTH_WARPS; ++w) t += whist[w * 256 + tid];
+            hist[tid] = t;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // lane l owns the bins 255 - 8 l ... 248 - 8 l (descending); keys above a lane's bins = exclusive prefix
+            const unsigned need = s_k;
+            unsigned own = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) own += hist[255 - 8 * lane - j];
+            unsigned incl = own;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
             }
-            s_k = need - run;
-            s_prefix = prefix | ((unsigned)b << shift);
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= need);   // the k-th key exists: some lane reaches `need`
+            const int owner = hit ? __ffs(hit) - 1 : 31;
+            if (lane == owner) {
+                unsigned run = incl - own;
+                int b = 255 - 8 * lane;
+                for (int j = 0; j < 7; ++j, --b) {
+                    if (run + hist[b] >= need) break;
+                    run += hist[b];
+                }
+                s_k = need - run;
+                s_prefix = prefix | ((unsigned)b << shift);
+            }
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[blockIdx.x] = ord2f(s_prefix);
+    if (tid == 0) out[blockIdx.x] = ord2f(s_prefix);
 }
 
 // y[n,m] = act(sum_k x[n,k]*W[m,k] + b[m]); act 0 = identity, 1 = 1 + tanh(.)   (one warp per output)
@@ -120,7 +168,12 @@ extern "C" int aoc_cond_phi_f32(const float* x, const float* w, const float* b, 
 extern "C" int aoc_kth_largest_f32(const float* vals, int N, int L, int k, float* out, cudaStream_t stream) {
     AOC_CHECK_ARG(vals && out, "null pointer");
     AOC_CHECK_ARG(N > 0 && L > 0 && k >= 1 && k <= L, "k must be in [1, L]");
-    kth_largest_kernel<<<N, 1024, 0, stream>>>(vals, L, k, out);
+    const size_t fixed = (size_t)(KTH_WARPS * 256 + 256) * sizeof(unsigned);
+    const int in_smem = fixed + (size_t)L * 4 <= 200 * 1024;
+    const size_t smem = fixed + (in_smem ? (size_t)L * 4 : 0);
+    static PerDeviceOnce attr;
+    if (attr.first()) cudaFuncSetAttribute(kth_largest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    kth_largest_kernel<<<N, KTH_THREADS, smem, stream>>>(vals, L, k, out, in_smem);
     return launch_status("aoc_kth_largest_f32");
 }
 

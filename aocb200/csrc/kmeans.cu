@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(KmCfg<NP, TILE>::THREADS, KmCfg<NP, TILE>::MIN
     int* start = reinterpret_cast<int*>(km_raw + Cfg::OFF_START);
     int* tstart = reinterpret_cast<int*>(km_raw + Cfg::OFF_TS);             // first tile of object o; [O] = total
 
+    __shared__ int ncnt[K];                                                  // rows per label of the previous round
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.x, G = gridDim.x;
     const int O = p.O;
@@ -145,7 +146,22 @@ __global__ void __launch_bounds__(KmCfg<NP, TILE>::THREADS, KmCfg<NP, TILE>::MIN
         const int k = p.kk[o];
         const long long* acc = p.acc + (size_t)((it + 2) % 3) * ACC_N + (size_t)o * K * EMB;    // buffer of round it-1
         const int* cnt = p.cnt + (size_t)((it + 2) % 3) * CNT_N + (size_t)o * K;
-        for (int i = tid; i < K * EMB; i += THREADS) {
+        // two L2 round trips per call instead of one per element: the label counts first, then every accumulator word
+        // of this thread in flight before the first conversion (the call is on the critical path between two grid barriers)
+        if (tid < K) ncnt[tid] = (it > 0 && tid < k) ? __ldcg(cnt + tid) : 0;
+        __syncthreads();
+        constexpr int PER = (K * EMB + THREADS - 1) / THREADS;
+        long long a[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * THREADS;
+            a[u] = 0;
+            if (it > 0 && i < K * EMB && ncnt[i / EMB] > 0) a[u] = __ldcg(acc + i);
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int i = tid + u * THREADS;
+            if (i >= K * EMB) break;
             const int j = i / EMB, c = i - j * EMB;
             const size_t ci = (size_t)o * K * EMB + i;
             float v = 0.f;
@@ -153,8 +169,8 @@ __global__ void __launch_bounds__(KmCfg<NP, TILE>::THREADS, KmCfg<NP, TILE>::MIN
                 if (it == 0) {
                     v = __ldg(p.S + (size_t)(p.meta[MAXO + o] + p.init_idx[o * K + j]) * EMB + c);
                 } else {
-                    const int n = __ldcg(cnt + j);
-                    v = n > 0 ? (float)km_from_fix(__ldcg(acc + i)) / (float)n : __ldcg(p.cent + ci);
+                    const int n = ncnt[j];
+                    v = n > 0 ? (float)km_from_fix(a[u]) / (float)n : __ldcg(p.cent + ci);
                 }
             }
             Cs[c * K + j] = v;
