@@ -143,6 +143,49 @@ __global__ void resize_bicubic_kernel(const float* __restrict__ x, float* __rest
     }
 }
 
+// Input edge of the eval loop (dataloaders/custom_transforms.py:387-463 MultiRestrictSize + :465-487 MultiToTensor): uint8
+// HWC frame -> cv2.resize(..., INTER_CUBIC) of the float image (A = -0.75, half-pixel centres src = (dst + 0.5) * scale - 0.5,
+// source indices clamped, horizontal pass then vertical pass) -> optional mirror (tmp[:, ::-1]) -> /255, -mean, /std ->
+// CHW float32.  One thread per output pixel, the three channels of a tap from one 3-byte read; with Ho == H and Wo == W the
+// transform does not resize (the reference hands the sample on unchanged) and this is the normalisation alone.
+__global__ void __launch_bounds__(256) prepare_frame_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int Wo,
+                                                            int flip, float m0, float m1, float m2, float s0, float s1,
+                                                            float s2, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ho * Wo) return;
+    const int yo = i / Wo, xo = i - yo * Wo;
+    const int xs = flip ? Wo - 1 - xo : xo;                       // the mirror is applied AFTER the resize
+    float r[3];
+    if (Ho == H && Wo == W) {
+        const uint8_t* px = img + ((size_t)yo * W + xs) * 3;
+        r[0] = (float)px[0]; r[1] = (float)px[1]; r[2] = (float)px[2];
+    } else {
+        const float sy = (float)((double)H / (double)Ho), sx = (float)((double)W / (double)Wo);
+        float fy = ((float)yo + 0.5f) * sy - 0.5f, fx = ((float)xs + 0.5f) * sx - 0.5f;
+        const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+        float wy[4], wx[4];
+        cubic_coeffs(fy - (float)iy, wy);
+        cubic_coeffs(fx - (float)ix, wx);
+        r[0] = r[1] = r[2] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = min(max(iy - 1 + j, 0), H - 1);
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xx = min(max(ix - 1 + k, 0), W - 1);
+                const uint8_t* px = img + ((size_t)yy * W + xx) * 3;
+                h0 += (float)px[0] * wx[k]; h1 += (float)px[1] * wx[k]; h2 += (float)px[2] * wx[k];
+            }
+            r[0] += h0 * wy[j]; r[1] += h1 * wy[j]; r[2] += h2 * wy[j];
+        }
+    }
+    const size_t plane = (size_t)Ho * Wo;
+    out[i] = (r[0] / 255.f - m0) / s0;                            // the transform's own order: /255, -mean, /std (IEEE divisions)
+    out[plane + i] = (r[1] / 255.f - m1) / s1;
+    out[2 * plane + i] = (r[2] / 255.f - m2) / s2;
+}
+
 // Nearest resize of a uint8 label map, PyTorch 'nearest' rule: src = min(floor(dst * (in/out)), in-1) in float.
 __global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ x, uint8_t* __restrict__ y, int Hi, int Wi,
                                          int Ho, int Wo, float sh, float sw) {
@@ -227,6 +270,16 @@ extern "C" int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int 
     resize_bicubic_kernel<<<blocks, 256, 0, stream>>>(x, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, ac_scale(Hi, Ho),
                                                       ac_scale(Wi, Wo));
     return launch_status("aoc_resize_bicubic_nhwc_f32");
+}
+
+extern "C" int aoc_prepare_frame_u8(const uint8_t* img_hwc, int H, int W, int Ho, int Wo, int flip, const float* mean3,
+                                    const float* std3, float* out_chw, cudaStream_t stream) {
+    AOC_CHECK_ARG(img_hwc && out_chw && mean3 && std3, "null pointer");
+    AOC_CHECK_ARG(H > 0 && W > 0 && Ho > 0 && Wo > 0, "bad dims");
+    AOC_CHECK_ARG(std3[0] != 0.f && std3[1] != 0.f && std3[2] != 0.f, "zero std");
+    prepare_frame_kernel<<<cdiv((long long)Ho * Wo, 256), 256, 0, stream>>>(img_hwc, H, W, Ho, Wo, flip, mean3[0], mean3[1],
+                                                                          mean3[2], std3[0], std3[1], std3[2], out_chw);
+    return launch_status("aoc_prepare_frame_u8");
 }
 
 extern "C" int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo,

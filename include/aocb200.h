@@ -158,6 +158,11 @@ int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi,
                                 int ldy, cudaStream_t stream);
 /* torch.cat along channels: copy a channel slice between buffers with different row strides */
 int aoc_copy_channels_f32(const float* x, float* y, long long rows, int C, int ldx, int ldy, cudaStream_t stream);
+/* input edge of the eval loop: MultiRestrictSize's cv2.resize(INTER_CUBIC) + optional mirror + MultiToTensor's /255, -mean,
+ * /std, HWC -> CHW (dataloaders/custom_transforms.py:387-463, :465-487) in one kernel.  img_hwc: uint8 [H][W][3] on the
+ * device; mean3 / std3: HOST arrays of 3 floats; out_chw: float [3][Ho][Wo].  Ho == H && Wo == W: no resize (as the transform). */
+int aoc_prepare_frame_u8(const uint8_t* img_hwc, int H, int W, int Ho, int Wo, int flip, const float* mean3,
+                         const float* std3, float* out_chw, cudaStream_t stream);
 /* F.interpolate(mode='nearest') on label maps (aocnet.py:128-135) */
 int aoc_resize_nearest_u8(const uint8_t* x, uint8_t* y, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
 /* the same for an int64 label map (torch.argmax output, eval_manager_mm.py:318-320), values clamped to 0..255 */

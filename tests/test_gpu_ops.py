@@ -313,3 +313,35 @@ def test_kmeans_sweep_cluster_num(eng, k):
     assert worst < (1e-4 if flips == 0 else 0.1)
     if k <= 16:
         assert flips == 0
+
+
+def test_prepare_frame(eng):
+    """Input edge of the eval loop (aocb200/io.py::prepare_frame = aoc_prepare_frame_u8) against tensors recorded from the
+    reference's own MultiRestrictSize (cv2.resize INTER_CUBIC + mirror) + MultiToTensor on random uint8 frames
+    (tests/golden/io_edges.npz): resized, mirrored and unresized cases.  cv2 evaluates the separable cubic in float with its
+    own summation order / SIMD, so agreement is to float rounding of the 0..255 image: observed 4.0e-5 after /255 and /std,
+    asserted x 1.5."""
+    import os
+    from aocb200 import io as aio
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "io_edges.npz"))
+    worst = 0.0
+    for k in range(int(g["n_frames"])):
+        img = g["frame%d_u8" % k]
+        kw = g["frame%d_kw" % k]
+        ns, flip = int(kw[1]), bool(kw[2])
+        sizes = aio.multi_restrict_size(img.shape[0], img.shape[1], None, float(kw[0]), [float(v) for v in kw[3:3 + ns]], flip)
+        assert len(sizes) == int(g["frame%d_n" % k])
+        for a, s in enumerate(sizes):
+            want = torch.from_numpy(g["frame%d_aug%d" % (k, a)])
+            assert bool(g["frame%d_aug%d_flip" % (k, a)]) == s["flip"]
+            got = aio.prepare_frame(img, (s["h"], s["w"]), s["flip"], device=eng.dev)
+            assert tuple(got.shape[1:]) == tuple(want.shape)
+            d = (got[0].cpu() - want).abs().max().item()
+            worst = max(worst, d)
+    print("[parity] prepare_frame vs the reference transforms (cv2 INTER_CUBIC + mirror + MultiToTensor): max|d| %.3e" % worst)
+    assert worst < 6e-5
+    # the whole augmentation list in one call, labels mirrored but never resized
+    lab = np.arange(70 * 90, dtype=np.int64).reshape(70, 90) % 7
+    smp = aio.prepare_samples(g["frame0_u8"], lab, None, 64, (1.0, 1.3), True, device=eng.dev)
+    assert [bool(s["flip"]) for s in smp] == [False, True, False, True]
+    assert torch.equal(smp[1]["label"], torch.flip(torch.from_numpy(lab), dims=[1])) and smp[0]["label"].shape == (70, 90)
