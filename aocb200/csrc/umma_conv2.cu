@@ -136,9 +136,24 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
 // the MAIN issuer's iteration -- barrier waits (~100 cycles per try_wait, not overlappable), tcgen05 fence, elect, the
 // uniform-register chain in front of each tcgen05 instruction, on a sub-partition shared with four busy warps -- took
 // ~385 cycles per stage, hence one full barrier per PAIR of stages for both operands and two stages per iteration.
-template <int TN, bool F16>
+// Halo variant (3x3, stride 1, pad = dilation = 1, split-fp16): output tiles of 16 rows x 8 columns; the raw halo patch
+// (18 x 10 pixels x 32 channels) of a channel box is loaded ONCE (not once per filter tap), transformed ONCE into
+// split-fp16 operand tiles in SHARED memory, and the nine taps of the box read that tile through nine descriptor start
+// addresses: K-major SWIZZLE_NONE core matrices = 8 consecutive pixels of a halo row x 8 channels (16 B per pixel), the
+// 8-row-group stride (SBO) is one halo row, the k-group stride (LBO) one pixel plane.
+constexpr int C2H_TH = 16, C2H_TW = 8;                           // output tile (rows x columns) = 128 pixels
+constexpr int C2H_D = 1;                                         // dilation (= padding) the shared-memory budget is sized for
+constexpr int C2H_P = (C2H_TH + 2 * C2H_D) * (C2H_TW + 2 * C2H_D);      // halo pixels (180)
+constexpr uint32_t C2H_RAW_BYTES = (C2H_P * 128 + 1023) / 1024 * 1024;  // raw halo box: P rows of 32 fp32, 1 KB aligned (swizzle)
+constexpr int C2H_NRAW = 3;                                      // raw halo ring depth
+constexpr uint32_t C2H_A_HALF = 4 * C2H_P * 16;                  // hi (or lo) operand tile of a box: 4 k-groups x P pixels x 16 B
+constexpr uint32_t C2H_A_BUF = 2 * C2H_A_HALF;                   // hi + lo
+
+template <int TN, bool F16, bool HALO = false>
 struct C2Cfg {
-    static constexpr int NR = C2_NS == 2 ? 6 : 7;            // raw activation ring depth (128 pixels x 32 channels each)
+    // raw activation ring depth (128 pixels x 32 channels each); halo: barrier index space -- slots 0..2 the raw halo ring,
+    // 3..4 the two operand-tile buffers
+    static constexpr int NR = HALO ? 5 : (C2_NS == 2 ? 6 : 7);
     // operand ring (activation half in TMEM, 32 columns per stage; weight half in shared memory): a weight chunk is
     // requested when the stage it replaces retires and needs an L2 round trip (~1.5k cycles) to land, so the period of
     // a stage cannot drop below (round trip + MMA time) / depth: 8 stages where TMEM has room (TN = 64), else 4
@@ -146,13 +161,14 @@ struct C2Cfg {
     static constexpr uint32_t B_BYTES = TN * C2_KC * (F16 ? 2 : 4) * 2;
     static constexpr uint32_t A_COLS = F16 ? 16 : 32;        // TMEM columns of one activation operand stage
     static constexpr uint32_t RAW_OFF = 0;
-    static constexpr uint32_t OP_OFF = NR * C2_RAW_BYTES;
+    static constexpr uint32_t A_OFF = C2H_NRAW * C2H_RAW_BYTES;                // halo: operand tiles [2 buffers][hi | lo]
+    static constexpr uint32_t OP_OFF = HALO ? A_OFF + 2 * C2H_A_BUF : NR * C2_RAW_BYTES;
     static constexpr uint32_t TAB_OFF = OP_OFF + NO * B_BYTES;
     static constexpr uint32_t STG_OFF = TAB_OFF + 2 * C2_MAX_AFFINE_C * 4;     // epilogue staging: 8 warps x 32 rows x 128 B
     static constexpr uint32_t BAR_OFF = STG_OFF + 8 * 4096;
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
-    static constexpr int NCB = TN <= 64 ? 2 : 1;             // CORR accumulators: double buffered across tiles when they fit
+    static constexpr int NCB = (TN <= 64 || HALO) ? 2 : 1;   // CORR accumulators: double buffered across tiles when they fit
     // correction issuers: one warp for both terms (TN = 128, the tensor pipe is the limit), or one warp and one
     // accumulator per term (TN = 64: a stage is only 192 tensor cycles, the ~75 cycles per tcgen05 instruction of an
     // issuing thread are the limit -- so the 6 MMAs of a stage are spread over three threads)
@@ -167,9 +183,10 @@ struct C2Cfg {
 // not carry them: a Tile kept in local memory cost 18 % on the large layers).
 struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0; };
 
-template <int TN, bool SK, bool F16>
-__global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
-    using Cfg = C2Cfg<TN, F16>;
+template <int TN, bool SK, bool F16, bool HALO = false>
+__global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
+    static_assert(!HALO || (F16 && !SK && C2_NS == 2), "the halo variant is split-fp16, unsplit, two transform warpgroups");
+    using Cfg = C2Cfg<TN, F16, HALO>;
     constexpr uint32_t C2_WCHUNK = c2_wchunk(F16);
     constexpr int C2_NR = Cfg::NR;
     constexpr int C2_NO = Cfg::NO, C2_NB = Cfg::NO;
@@ -242,8 +259,16 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
     // global memory first executes griddepcontrol.wait (= the previous grid has completed and its writes are visible).
     asm volatile("griddepcontrol.launch_dependents;");
     if (warp == C2_XW + 9 && lane == 0) {
-        for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
-        for (int q = 0; q < C2_NO / 2; ++q) { mbar_init(OP_FULL(q), 10); mbar_init(OP_EMPTY(q), 1 + NCI); }
+        if (HALO) {
+            // RAW_FULL(0..2) / RAW_EMPTY(0..2): raw halo ring (released by the eight transform warps); RAW_FULL(3 + b) /
+            // RAW_EMPTY(3 + b): operand-tile buffer b full (eight transform warps) / empty (both issuers' commits)
+            for (int s = 0; s < C2H_NRAW; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 8); }
+            for (int b = 0; b < 2; ++b) { mbar_init(RAW_FULL(3 + b), 8); mbar_init(RAW_EMPTY(3 + b), 1 + NCI); }
+            for (int q = 0; q < C2_NO / 2; ++q) { mbar_init(OP_FULL(q), 2); mbar_init(OP_EMPTY(q), 1 + NCI); }   // weights only
+        } else {
+            for (int s = 0; s < C2_NR; ++s) { mbar_init(RAW_FULL(s), 1); mbar_init(RAW_EMPTY(s), 4); }
+            for (int q = 0; q < C2_NO / 2; ++q) { mbar_init(OP_FULL(q), 10); mbar_init(OP_EMPTY(q), 1 + NCI); }
+        }
         for (int b = 0; b < 2; ++b) {
             mbar_init(MAIN_FULL(b), 1); mbar_init(MAIN_EMPTY(b), 8); mbar_init(CORR_EMPTY(b), 8); mbar_init(CORR_FULL(b), NCI);
         }
@@ -261,6 +286,97 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
 
     if (warp < C2_XW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
+        if constexpr (HALO) {
+            // ===== halo transform: all eight warps convert the raw halo patch of a channel box (P pixels x 32 channels) ONCE
+            // into the split-fp16 operand tiles [k-group of 8 channels][pixel][16 B] (hi and lo); item = (pixel, k-group) =====
+            const int d = p.dil;
+            const int HWd = C2H_TW + 2 * d, P = HWd * (C2H_TH + 2 * d);
+            const uint32_t a0 = smem_u32(smem + Cfg::A_OFF);
+            const uint32_t tab_s = smem_u32(tab_a);
+            const bool need_mask = p.in_b != nullptr;
+            int sr = 0, ab = 0;
+            uint32_t pr = 0, pa0 = 0, pa1 = 0;
+            int tab_n = -1;
+            float amax = 0.f;
+            for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+                const Tile tl = decode(t);
+                if (affine && tl.n != tab_n) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
+                    const int cpad = p.ncc * C2_KC;
+                    for (int c = threadIdx.x; c < cpad; c += C2_XT) {
+                        const bool ok = c < p.Cin;
+                        tab_a[c] = ok ? (p.in_a ? __ldg(p.in_a + (size_t)tl.n * p.Cin + c) : 1.f) : 0.f;
+                        tab_b[c] = (ok && p.in_b) ? __ldg(p.in_b + (size_t)tl.n * p.Cin + c) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
+                    tab_n = tl.n;
+                }
+                const int hy0 = tl.ho0 - d, hx0 = tl.wo0 - d;             // image position of halo pixel (0, 0): stride 1, pad = d
+                for (int cb = 0; cb < nrc; ++cb) {
+                    const int nq = (2 * cb + 1 < p.ncc) ? 4 : 2;          // k-groups of this box (an odd stage count: half a box)
+                    mbar_wait(RAW_FULL(sr), pr);
+                    if (ab == 0) { mbar_wait(RAW_EMPTY(3), pa0 ^ 1u); pa0 ^= 1u; }
+                    else         { mbar_wait(RAW_EMPTY(4), pa1 ^ 1u); pa1 ^= 1u; }
+                    const uint32_t rawb = raw0 + sr * C2H_RAW_BYTES;
+                    const uint32_t ahi = a0 + ab * C2H_A_BUF, alo = ahi + C2H_A_HALF;
+                    for (int i = threadIdx.x; i < nq * P; i += C2_XT) {
+                        const int q = (i >= P) + (i >= 2 * P) + (i >= 3 * P);
+                        const int pp = i - q * P;
+                        float v[8];
+                        const uint32_t row = rawb + (uint32_t)(pp * 128), sw = (uint32_t)(pp & 7);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3])
+                                         : "r"(row + ((((uint32_t)(2 * q + j)) ^ sw) << 4)));
+                        if (affine) {
+                            const uint32_t tc = tab_s + (uint32_t)((cb * C2_RKC + q * 8) * 4);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                float4 a4, b4;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(tc + j * 16));
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(tc + C2_MAX_AFFINE_C * 4 + j * 16));
+                                ffma2(v[4 * j], v[4 * j + 1], a4.x, a4.y, b4.x, b4.y);
+                                ffma2(v[4 * j + 2], v[4 * j + 3], a4.z, a4.w, b4.z, b4.w);
+                            }
+                            if (p.in_relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                            }
+                            if (need_mask) {                                 // zero padding applies AFTER the affine
+                                const int py = pp / HWd, px = pp - py * HWd;
+                                const bool ok = (unsigned)(hy0 + py) < (unsigned)p.H && (unsigned)(hx0 + px) < (unsigned)p.W;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = ok ? v[e] : 0.f;
+                            }
+                        }
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float d0, d1;
+                            asm("max.abs.f32 %0, %0, %1, %2;" : "+f"(amax) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+                            asm("{\n\t.reg .b16 e0, e1;\n\tmov.b32 {e0, e1}, %2;\n\t"
+                                "sub.rn.f32.f16 %0, e0, %3;\n\tsub.rn.f32.f16 %1, e1, %4;\n\t}"
+                                : "=f"(d0), "=f"(d1) : "r"(h[j]), "f"(v[2 * j]), "f"(v[2 * j + 1]));
+                            fmul2(d0, d1, -2048.f);
+                            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(d1), "f"(d0));
+                        }
+                        const uint32_t off = (uint32_t)((q * P + pp) * 16);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ahi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(alo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+                    }
+                    fence_proxy_async();                                     // generic-proxy stores -> tcgen05.mma operand reads
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(RAW_FULL(3 + ab)); mbar_arrive(RAW_EMPTY(sr)); }
+                    if (++sr == C2H_NRAW) { sr = 0; pr ^= 1u; }
+                    ab ^= 1;
+                }
+            }
+            if (p.overflow && amax >= 6.0e4f) *p.overflow = 1;
+        } else {
         // ===== transform warps: two sets of four (set g owns the operand stages with an even / odd running index, so a
         // set's per-stage instruction stream -- ~550 cycles -- has two stage-times to complete); thread <-> pixel row <->
         // TMEM lane; 16 raw channels -> hi/lo -> tcgen05.st =====
@@ -430,6 +546,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         // cvt.rn.satfinite clamps at 65504: a clamped operand means a wrong result, so it is reported (sticky word; the
         // host re-runs the frame with 3xTF32 operands, which have the fp32 exponent range)
         if (F16 && p.overflow && amax >= 6.0e4f) *p.overflow = 1;
+        }
     } else if (warp < C2_XW + 8) {
         // ===== drain warps: MAIN accumulator chunks -> fp32 registers (round-to-nearest adds), then epilogue =====
         // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
@@ -680,6 +797,20 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
             uint32_t pr = 0;
+            if constexpr (HALO) {
+                // halo: ONE box per 32-channel group -- the (16 + 2d) x (8 + 2d) pixel patch all nine taps read
+                const uint32_t bytes = (uint32_t)((C2H_TW + 2 * p.dil) * (C2H_TH + 2 * p.dil) * 128);
+                for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+                    const Tile tl = decode(t);
+                    for (int cb = 0; cb < nrc; ++cb) {
+                        mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
+                        C2_TRACE(0, 18 * cb);
+                        mbar_arrive_expect_tx(RAW_FULL(sr), bytes);
+                        tma_load_4d(raw0 + sr * C2H_RAW_BYTES, &tmapA, cb * C2_RKC, tl.wo0 - p.dil, tl.ho0 - p.dil, tl.n, RAW_FULL(sr));
+                        if (++sr == C2H_NRAW) { sr = 0; pr ^= 1u; }
+                    }
+                }
+            } else
             for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
                 const Tile tl = decode(t);
                 const int wbase = tl.wo0 * p.stride - p.pad, hbase = tl.ho0 * p.stride - p.pad;
@@ -714,7 +845,15 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
                 const int rb = tl.n0 / C2_WRB;
                 const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
-                for (int it = tl.it0; it < tl.it1; ++it) {
+                // halo: the K loop runs (channel box, tap, half box) instead of (tap, stage); the packed image keeps its order
+                int h_cb = 0, h_tap = 0, h_half = 0;
+                for (int it_ = tl.it0; it_ < tl.it1; ++it_) {
+                    int it = it_;
+                    if (HALO) {
+                        it = h_tap * p.ncc + 2 * h_cb + h_half;
+                        const int nh = (2 * h_cb + 1 < p.ncc) ? 2 : 1;
+                        if (++h_half == nh) { h_half = 0; if (++h_tap == 9) { h_tap = 0; ++h_cb; } }
+                    }
                     if ((sb_ & 1) == 0) mbar_wait(OP_EMPTY(sb_ >> 1), pb ^ 1u);
                     C2_TRACE(8, it);
                     const uint32_t bfull = OP_FULL(sb_ >> 1);
@@ -745,6 +884,55 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, b = 0;
         uint32_t po = 0, pe0 = 0, pe1 = 0;
+        if constexpr (HALO) {
+            // halo: the A operand is the transformed halo tile in shared memory; tap (r, s) of a box = the same tile read from
+            // the start address of halo pixel (r d, s d): 16 groups of 8 rows (= 8 consecutive pixels of a halo row, 16 B
+            // each) one halo row apart (SBO), the two k-groups of a stage one pixel plane apart (LBO)
+            const int d = p.dil;
+            const int HWd = C2H_TW + 2 * d, P = HWd * (C2H_TH + 2 * d);
+            const uint32_t a0 = smem_u32(smem + Cfg::A_OFF);
+            int ab = 0;
+            uint32_t pf0 = 0, pf1 = 0;
+            for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+                int in_chunk = 0, it = 0;
+                for (int cb = 0; cb < nrc; ++cb) {
+                    const int nh = (2 * cb + 1 < p.ncc) ? 2 : 1;
+                    if (ab == 0) { mbar_wait(RAW_FULL(3), pf0); pf0 ^= 1u; }
+                    else         { mbar_wait(RAW_FULL(4), pf1); pf1 ^= 1u; }
+                    const uint32_t ahi = a0 + ab * C2H_A_BUF;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int tr = tap / 3, ts = tap - 3 * tr;
+                        const uint32_t tapoff = (uint32_t)((tr * d * HWd + ts * d) * 16);
+                        for (int half = 0; half < nh; ++half, ++it) {
+                            if (lane == 0) C2_TRACE(5, it);
+                            if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);      // the weights of both stages of the pair
+                            if (lane == 0) C2_TRACE(6, it);
+                            const int bb = b, ic = in_chunk;
+                            if (in_chunk == 0) {
+                                if (b == 0) { mbar_wait(MAIN_EMPTY(0), pe0 ^ 1u); pe0 ^= 1u; }
+                                else        { mbar_wait(MAIN_EMPTY(1), pe1 ^ 1u); pe1 ^= 1u; }
+                            }
+                            const bool ls = (in_chunk + 1 == p.chunk) || (it == nIt - 1);
+                            if (ls) { b ^= 1; in_chunk = 0; } else { ++in_chunk; }
+                            const bool box_end = tap == 8 && half == nh - 1;
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t sb = op0 + so * Cfg::B_BYTES;
+                                const uint64_t adesc = smem_desc(ahi + tapoff + (uint32_t)(half * 2 * P * 16), (uint32_t)(P * 16), (uint32_t)(HWd * 16));
+                                mma_f16(tb + (uint32_t)(bb * TN), adesc, smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, ic > 0 ? 1u : 0u);
+                                if (so & 1) mma_commit(OP_EMPTY(so >> 1));
+                                if (ls) mma_commit(MAIN_FULL(bb));
+                                if (box_end) mma_commit(RAW_EMPTY(3 + ab));      // this issuer is done with the operand tile
+                            }
+                            __syncwarp();
+                            if (lane == 0) C2_TRACE(7, it);
+                            if (++so == C2_NO) { so = 0; po ^= 1u; }
+                        }
+                    }
+                    ab ^= 1;
+                }
+            }
+        } else
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const Tile tl = decode(t);
             int in_chunk = 0;
@@ -808,6 +996,52 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16>::THREADS, 1) conv2_kernel(const
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         int so = 0, cb = 0;
         uint32_t po = 0, pc0 = 0, pc1 = 0;
+        if constexpr (HALO) {
+            const int d = p.dil;
+            const int HWd = C2H_TW + 2 * d, P = HWd * (C2H_TH + 2 * d);
+            const uint32_t a0 = smem_u32(smem + Cfg::A_OFF);
+            int ab = 0;
+            uint32_t pf0 = 0, pf1 = 0;
+            for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+                const uint32_t d_corr = tb + (uint32_t)((2 + cb) * TN);
+                if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
+                else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
+                int it = 0;
+                for (int bx = 0; bx < nrc; ++bx) {
+                    const int nh = (2 * bx + 1 < p.ncc) ? 2 : 1;
+                    if (ab == 0) { mbar_wait(RAW_FULL(3), pf0); pf0 ^= 1u; }
+                    else         { mbar_wait(RAW_FULL(4), pf1); pf1 ^= 1u; }
+                    const uint32_t ahi = a0 + ab * C2H_A_BUF, alo = ahi + C2H_A_HALF;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int tr = tap / 3, ts = tap - 3 * tr;
+                        const uint32_t tapoff = (uint32_t)((tr * d * HWd + ts * d) * 16);
+                        for (int half = 0; half < nh; ++half, ++it) {
+                            if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);
+                            if (lane == 0) C2_TRACE(9, it);
+                            const bool box_end = tap == 8 && half == nh - 1;
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t sb = op0 + so * Cfg::B_BYTES;
+                                const uint32_t koff = tapoff + (uint32_t)(half * 2 * P * 16);
+                                // lo(A) * hi(B), then hi(A) * lo(B): weight stage = [hi block | lo block] of TN rows x 32 B
+                                mma_f16(d_corr, smem_desc(alo + koff, (uint32_t)(P * 16), (uint32_t)(HWd * 16)),
+                                        smem_desc(sb, LBO_BYTES, SBO_BYTES), idesc, it > 0 ? 1u : 0u);
+                                mma_f16(d_corr, smem_desc(ahi + koff, (uint32_t)(P * 16), (uint32_t)(HWd * 16)),
+                                        smem_desc(sb + TN * 32, LBO_BYTES, SBO_BYTES), idesc, 1u);
+                                if (so & 1) mma_commit(OP_EMPTY(so >> 1));
+                                if (it == nIt - 1) mma_commit(CORR_FULL(cb));
+                                if (box_end) mma_commit(RAW_EMPTY(3 + ab));
+                            }
+                            __syncwarp();
+                            if (lane == 0) C2_TRACE(10, it);
+                            if (++so == C2_NO) { so = 0; po ^= 1u; }
+                        }
+                    }
+                    ab ^= 1;
+                }
+                cb ^= 1;
+            }
+        } else
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
             const uint32_t d_corr = tb + (uint32_t)((2 + ci * NCB + cb) * TN);
             // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
@@ -998,6 +1232,31 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     return launch_status("aoc_conv2d_nhwc_tc");
 }
 
+// halo variant: no split-K (the launcher only takes it for layers with at least one tile per SM)
+template <int TN>
+static int launch_conv2_halo(const CUtensorMap& map, const Conv2P& p, int tiles, cudaStream_t stream) {
+    using Cfg = C2Cfg<TN, true, true>;
+    static_assert(Cfg::SMEM <= 232448, "shared memory of the halo variant");
+    static PerDeviceOnce attr;
+    if (attr.first())
+        cudaFuncSetAttribute(conv2_kernel<TN, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    Conv2P q = p;
+    q.tiles_n = cdiv(p.Cout, TN);
+    q.total_tiles = tiles * q.tiles_n;
+    q.ksplit = 1; q.ws = nullptr; q.ws_cnt = nullptr;
+    const int sms = device_sms();
+    const int grid = q.total_tiles < sms ? q.total_tiles : sms;
+    cudaLaunchAttribute attr_pdl[1];
+    attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr_pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false, true, true>, map, q);
+    return launch_status("aoc_conv2d_nhwc_tc (halo)");
+}
+
+int g_conv_halo = 1;    // aoc_set_option("conv_halo", 0/1): halo variant for the 3x3 / stride-1 layers that fill the chip
 int g_conv_chunk = 8;   // aoc_set_option("conv_chunk", stages): default accumulation chain length
 int g_conv_dbg = 0;     // aoc_set_option("conv_dbg", bits): ablation switches, honoured by the tooling build only (C2_DBG)
 unsigned long long* g_conv_trace = nullptr;
@@ -1026,6 +1285,15 @@ extern "C" int aoc_conv_pack_weights(const float* w, int Cout, int Cin, int kh, 
     else
         conv2_pack_weights_kernel<<<blocks, 256, 0, stream>>>(w, Cout, Cin, kh * kw, ncc, rows_padded, (uint8_t*)w_packed);
     return launch_status("aoc_conv_pack_weights");
+}
+
+// does this layer run the halo variant?  3x3, stride 1, pad = dilation <= C2H_D, split-fp16 operands, and at least one
+// 16 x 8 tile per SM (smaller layers keep the per-tap kernel and its split-K schedule)
+static bool conv_use_halo(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int operand_mode) {
+    if (!g_conv_halo || operand_mode != AOC_CONV_SPLIT_F16) return false;
+    if (kh != 3 || kw != 3 || stride != 1 || dil < 1 || dil > C2H_D || pad != dil) return false;
+    const long long tiles = (long long)N * cdiv(W, C2H_TW) * cdiv(H, C2H_TH) * cdiv(Cout, Cout <= 64 ? 64 : 128);
+    return tiles >= device_sms();
 }
 
 // pixel-patch geometry shared by the launcher and the tile-statistics consumers
@@ -1058,10 +1326,12 @@ extern "C" int aoc_conv_trace(void* device_buffer_16x256_u64) {
     return AOC_OK;
 }
 
-extern "C" int aoc_conv_tiles_per_image(int H, int W, int kh, int kw, int stride, int pad, int dil) {
+extern "C" int aoc_conv_tiles_per_image(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+                                        int operand_mode) {
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
     if (Ho <= 0 || Wo <= 0) return 0;
+    if (conv_use_halo(N, H, W, Cout, kh, kw, stride, pad, dil, operand_mode)) return 4 * cdiv(Wo, C2H_TW) * cdiv(Ho, C2H_TH);
     return 4 * cdiv(Wo, 1 << l2) * cdiv(Ho, C2_BM >> l2);     // one statistics row per 32-pixel quadrant of a 128-pixel tile
 }
 
@@ -1101,6 +1371,8 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.overflow = overflow_flag;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
+    const bool halo = conv_use_halo(N, H, W, Cout, kh, kw, stride, pad, dil, operand_mode);
+    if (halo) best_l2 = 3;                                            // 16 rows x 8 columns
     p.tw_log2 = best_l2;
     p.th = C2_BM >> best_l2;
     const int tw = 1 << best_l2;
@@ -1110,6 +1382,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)gW, (cuuint64_t)gH, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)gW * ldx * 4, (cuuint64_t)gH * gW * ldx * 4};
     cuuint32_t box[4] = {(cuuint32_t)C2_RKC, (cuuint32_t)(tw * stride), (cuuint32_t)(p.th * stride), 1u};
+    if (halo) { box[1] = (cuuint32_t)(C2H_TW + 2 * dil); box[2] = (cuuint32_t)(C2H_TH + 2 * dil); }
     cuuint32_t estr[4] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u};
     CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1125,6 +1398,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     // thread fit since the warpgroups re-partition the register file).  Layers with few pixel tiles are spread over the
     // SMs by split-K, not by narrower tiles.
     const bool narrow = Cout <= 64 || p.nIt < g_conv_narrow_nit;
+    if (halo) return Cout <= 64 ? launch_conv2_halo<64>(map, p, tiles, stream) : launch_conv2_halo<128>(map, p, tiles, stream);
     if (g_conv_f16)
         return narrow ? launch_conv2<64, true>(map, p, tiles, workspace, ws_bytes, stream)
                       : launch_conv2<128, true>(map, p, tiles, workspace, ws_bytes, stream);

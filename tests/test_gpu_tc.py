@@ -205,3 +205,30 @@ def test_global_match_tc_vs_simt(eng, f16):
         eng.tc_match = True
         report("global match tcgen05 vs simt (seed %d)" % seed, outs[True], outs[False], 5e-6)
     eng.L.set_option(b"match_f16", 1)
+
+
+def test_conv_tc_halo_variant(eng):
+    """The halo variant of the convolution (3x3, stride 1, pad = dilation = 1, at least one 16 x 8 tile per SM: the halo
+    patch of a channel box is transformed once and the nine taps read it through shifted shared-memory descriptors) against
+    float64, on shapes that exercise: an odd number of 16-channel stages (half a channel box), ragged borders in both
+    directions, Cout = 64 / 96 / 256, the fused input affine with shift (zero padding must stay zero) + ReLU, residual, bias,
+    output ReLU and the statistics rows; and against the per-tap kernel on the same inputs."""
+    eng.tc_conv = True
+    c = _conv_tc_case
+    L = eng.L
+    assert L.set_option(b"conv_halo", 1) == 0
+    cases = [dict(N=3, H=70, W=90, Cin=48, Cout=96, seed=201, relu=True),                     # ncc = 3 (odd), Cout % 128 != 0
+             dict(N=6, H=61, W=107, Cin=64, Cout=64, seed=202, scale=True, shift=True, in_relu=True, bias=False),
+             dict(N=1, H=121, W=213, Cin=128, Cout=256, seed=203, res=True, relu=True),
+             dict(N=4, H=50, W=75, Cin=320, Cout=128, seed=204, bias=False)]
+    for kw in cases:
+        kw = dict(kw)
+        N, H, W, Cin, Cout = (kw.pop(k) for k in ("N", "H", "W", "Cin", "Cout"))
+        assert L.conv_tiles_per_image(N, H, W, Cout, 3, 3, 1, 1, 1, 1) == 4 * ((W + 7) // 8) * ((H + 15) // 16), "halo not selected"
+        e_h, e32 = c(eng, N, H, W, Cin, Cout, 3, 1, 1, 1, **kw)
+        L.set_option(b"conv_halo", 0)
+        try:
+            e_t, _ = c(eng, N, H, W, Cin, Cout, 3, 1, 1, 1, **kw)
+        finally:
+            L.set_option(b"conv_halo", 1)
+        print("[parity]    halo %.3e   per-tap %.3e   cpu fp32 %.3e" % (e_h, e_t, e32))
