@@ -85,8 +85,9 @@ struct Conv2P {
 
 #ifdef AOC_CONV_TRACE   // tooling build only (tools/conv_trace.py): keeps the production kernel's code small
 // stage index of an event = running stage count of CTA 0 (tile ordinal x stages per tile + stage): short-K layers show several tiles
-#define C2_TRACE(ev, st) do { const int st_ = (t - (int)blockIdx.x) / (int)gridDim.x * nIt + (st); \
-                              if (p.trace && blockIdx.x == 0 && st_ < 256) p.trace[(ev) * 256 + st_] = clock64(); } while (0)
+#define C2_TRACE(ev, st) do { if (p.trace && blockIdx.x == 0) { \
+                                  const int st_ = __float2int_rd(((float)t + 0.5f) * c2_inv_grid) * nIt + (st); \
+                                  if (st_ < 256) p.trace[(ev) * 256 + st_] = clock64(); } } while (0)
 // ablation switches of the tooling build (aoc_set_option("conv_dbg", bits); results are garbage, the timing is the point):
 // 1 no weight copies (the barrier is completed by a plain arrive), 2 no activation TMA, 4 no correction MMAs,
 // 8 no transform arithmetic (zeros are stored), 16 no main MMAs
@@ -217,6 +218,9 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
     const uint32_t op0 = smem_u32(smem + Cfg::OP_OFF);
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+#ifdef AOC_CONV_TRACE
+    const float c2_inv_grid = 1.0f / (float)gridDim.x;       // tile ordinal of CTA 0 without an integer division per event
+#endif
     const int tw_mask = (1 << p.tw_log2) - 1;
     const int tpi = p.tiles_x * p.tiles_y;
     const bool affine = p.in_a != nullptr || p.in_b != nullptr || p.in_relu;
@@ -1289,7 +1293,8 @@ extern "C" int aoc_conv_pack_weights(const float* w, int Cout, int Cin, int kh, 
 
 // does this layer run the halo variant?  3x3, stride 1, pad = dilation <= C2H_D, split-fp16 operands, and at least one
 // 16 x 8 tile per SM (smaller layers keep the per-tap kernel and its split-K schedule)
-static bool conv_use_halo(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int operand_mode) {
+static bool conv_use_halo(int N, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int dil, int operand_mode) {
+    (void)Cin;
     if (!g_conv_halo || operand_mode != AOC_CONV_SPLIT_F16) return false;
     if (kh != 3 || kw != 3 || stride != 1 || dil < 1 || dil > C2H_D || pad != dil) return false;
     const long long tiles = (long long)N * cdiv(W, C2H_TW) * cdiv(H, C2H_TH) * cdiv(Cout, Cout <= 64 ? 64 : 128);
@@ -1326,12 +1331,12 @@ extern "C" int aoc_conv_trace(void* device_buffer_16x256_u64) {
     return AOC_OK;
 }
 
-extern "C" int aoc_conv_tiles_per_image(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
+extern "C" int aoc_conv_tiles_per_image(int N, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int dil,
                                         int operand_mode) {
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
     if (Ho <= 0 || Wo <= 0) return 0;
-    if (conv_use_halo(N, H, W, Cout, kh, kw, stride, pad, dil, operand_mode)) return 4 * cdiv(Wo, C2H_TW) * cdiv(Ho, C2H_TH);
+    if (conv_use_halo(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, operand_mode)) return 4 * cdiv(Wo, C2H_TW) * cdiv(Ho, C2H_TH);
     return 4 * cdiv(Wo, 1 << l2) * cdiv(Ho, C2_BM >> l2);     // one statistics row per 32-pixel quadrant of a 128-pixel tile
 }
 
@@ -1371,7 +1376,7 @@ extern "C" int aoc_conv2d_nhwc_tc(const float* x, const void* w_packed, const fl
     p.overflow = overflow_flag;
     p.vec_out = (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) && (!residual || (ldres % 4 == 0 && ((uintptr_t)residual & 15) == 0));
     p.H = gH; p.W = gW; p.Ho = Ho; p.Wo = Wo;
-    const bool halo = conv_use_halo(N, H, W, Cout, kh, kw, stride, pad, dil, operand_mode);
+    const bool halo = conv_use_halo(N, H, W, Cin, Cout, kh, kw, stride, pad, dil, operand_mode);
     if (halo) best_l2 = 3;                                            // 16 rows x 8 columns
     p.tw_log2 = best_l2;
     p.th = C2_BM >> best_l2;

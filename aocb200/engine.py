@@ -281,7 +281,7 @@ class Engine:
                 self._wpacked[name] = wp
             ts = None
             if stats:
-                tpi = self.L.conv_tiles_per_image(x.N, x.H, x.W, Cout, kh, kw, stride, pad, dil, mode)
+                tpi = self.L.conv_tiles_per_image(x.N, x.H, x.W, Cin, Cout, kh, kw, stride, pad, dil, mode)
                 ts = self.empty(x.N * tpi * 2 * Cout)
             wsp, wsn = None, 0
             if x.N * Ho * Wo <= 128 * 74 and not stats:       # few pixel tiles: let the library split K

@@ -96,7 +96,8 @@ size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh, int kw, i
  * per-channel sum and sum of squares of the stored output -- the GroupNorm / GCT statistics of the next layer come
  * out of the convolution epilogue instead of a second pass over the tensor (aoc_tile_stats_reduce_f32 folds them into
  * the [N][2][C] double layout of aoc_channel_stats_f32). */
-int aoc_conv_tiles_per_image(int N, int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil, int operand_mode);
+int aoc_conv_tiles_per_image(int N, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int dil,
+                             int operand_mode);
 /* tooling: when non-null, CTA 0 of every later aoc_conv2d_nhwc_tc launch records clock64() of its pipeline events
  * (8 events x the first 256 stages, uint64) into this device buffer; see tools/conv_trace.py.  NULL switches it off. */
 int aoc_conv_trace(void* device_buffer_16x256_u64);

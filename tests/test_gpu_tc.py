@@ -224,7 +224,7 @@ def test_conv_tc_halo_variant(eng):
     for kw in cases:
         kw = dict(kw)
         N, H, W, Cin, Cout = (kw.pop(k) for k in ("N", "H", "W", "Cin", "Cout"))
-        assert L.conv_tiles_per_image(N, H, W, Cout, 3, 3, 1, 1, 1, 1) == 4 * ((W + 7) // 8) * ((H + 15) // 16), "halo not selected"
+        assert L.conv_tiles_per_image(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, 1) == 4 * ((W + 7) // 8) * ((H + 15) // 16), "halo not selected"
         e_h, e32 = c(eng, N, H, W, Cin, Cout, 3, 1, 1, 1, **kw)
         L.set_option(b"conv_halo", 0)
         try:
