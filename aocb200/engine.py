@@ -199,6 +199,10 @@ class Engine:
         self.conv_chunk = int(os.environ.get("AOCB200_CONV_CHUNK", "0"))   # 0 = library default
         self._meta_host = torch.empty(META_INTS, dtype=torch.int32).pin_memory()
         self.use_graphs = os.environ.get("AOCB200_GRAPHS", "1") != "0"
+        # segment F (bank-dependent: 15 kernels) as a graph that is re-captured when the bank grows, or as plain launches
+        # (default: plain launches -- 15 kernels, ~40 us of host time per frame, nothing to re-capture at a bank change; the
+        # re-capture cost 0.3 ms per change and, sporadically, a 50-120 ms stall of the instantiation)
+        self.segf_graph = os.environ.get("AOCB200_SEGF_GRAPH", "0") != "0"
         self._segA, self._static = {}, {}
         self._cap_stream = self._pool = None
         self._gt_cache = (None, 0, 0)
@@ -245,6 +249,18 @@ class Engine:
     def new(self, N, H, W, C):
         return T(self.empty(N * H * W * C), N, H, W, C)
 
+    def grow(self, name, n, dtype):
+        """persistent typed buffer of at least n elements, grown geometrically (bank-sized arrays: object-sorted rows, row
+        maps); contents are not preserved"""
+        b = self._ws.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            if b is not None:
+                self._ws_keep.append(b)
+                n = max(int(n), 2 * b.numel())
+            b = torch.empty(int(n), dtype=dtype, device=self.dev)
+            self._ws[name] = b
+        return b
+
     def ws(self, name, nbytes, zero_head=0):
         """persistent scratch (never handed to the caller); zero_head: bytes at the front that the library expects zeroed
         when it first sees the buffer (split-K arrival counters) -- cleared once, at allocation"""
@@ -252,7 +268,8 @@ class Engine:
         if b is None or b.numel() < nbytes:
             if b is not None:
                 self._ws_keep.append(b)      # a captured graph may still point at the superseded buffer
-            b = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+                nbytes = max(int(nbytes), 2 * b.numel())     # geometric growth: a growing bank must not pay a cudaMalloc
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)   # (tens of ms, device-synchronising) per step
             if zero_head:
                 self.L.fill_u32(b.data_ptr(), 0, zero_head // 4, self.stream)
             self._ws[name] = b
@@ -517,8 +534,8 @@ class Engine:
         total = F * hw
         meta = self.empty(META_INTS, torch.int32)
         cap_rows = total + O * BANK_ALIGN
-        row_src = self.empty(cap_rows, torch.int32)
-        nat2sorted = self.empty(max(total, 1), torch.int32)
+        row_src = self.grow("bank.row_src", cap_rows, torch.int32)
+        nat2sorted = self.grow("bank.nat2sorted", max(total, 1), torch.int32)
         nws = L.bank_workspace_bytes(total, O)
         L.bank_index_build(bk.ids_all.data_ptr(), total, O, BANK_ALIGN, meta.data_ptr(), row_src.data_ptr(), cap_rows,
                            nat2sorted.data_ptr(), self.ws("bank", nws).data_ptr(), nws, st)
@@ -527,8 +544,8 @@ class Engine:
         mh = self._meta_host.numpy().copy()
         counts = [int(mh[o]) for o in range(O)]
         rows = int(mh[2 * MAXO + 1])
-        S = self.empty(max(rows, 1) * EMB)
-        r2 = self.empty(max(rows, 1))
+        S = self.grow("bank.S", max(rows, 1) * EMB, torch.float32)       # rebuilt in place: the stream was just drained, and a
+        r2 = self.grow("bank.r2", max(rows, 1), torch.float32)          # graph of the previous bank version is never replayed again
         L.bank_gather_f32(bk.emb_all.data_ptr(), row_src.data_ptr(), rows, S.data_ptr(), r2.data_ptr(), st)
         ix = dict(version=bk.version, O=O, total=total, meta=meta, mh=mh, counts=counts, rows=rows, S=S, r2=r2,
                   nat2sorted=nat2sorted, maxrows=max(counts) if counts else 0, hw=hw)
@@ -678,8 +695,9 @@ class Engine:
         prev_ids = self._label_ids(prev_mask, h, w)
         x = self._match_back(emb, g, P, pvalid, head, prev_e, prev_ids, O)
         if self.keep_debug:
-            self.debug.update(labels=labels, cent=cent, meta=ix["mh"].copy(), S=ix["S"], r2=ix["r2"],
-                              nat2sorted=ix["nat2sorted"], kk=kk, init=init)
+            rows_ = max(ix["rows"], 1)                    # (the bank arrays are capacity buffers: views of the live part)
+            self.debug.update(labels=labels, cent=cent, meta=ix["mh"].copy(), S=ix["S"][:rows_ * EMB], r2=ix["r2"][:rows_],
+                              nat2sorted=ix["nat2sorted"][:max(ix["total"], 1)], kk=kk, init=init)
         return x, head, prev_ids
 
     # ------------------------------------------------------------------ calibration decoder (decoding_module.py)
@@ -1087,8 +1105,8 @@ class Engine:
             return logits, mem, probs, label, conf
 
         # ---- segment F: bank-dependent (global matching, k-means proxies, bank heads)
-        if ix["rows"] == 0:
-            front()                                          # degenerate empty bank: plain launches
+        if ix["rows"] == 0 or not self.segf_graph:
+            front()                                          # degenerate empty bank / AOCB200_SEGF_GRAPH=0: plain launches
         else:
             segF = st["segF"]
             if segF is None or segF["version"] != ix["version"] or segF["emb"] is not emb:
