@@ -170,9 +170,11 @@ struct C2Cfg {
     static constexpr uint32_t SMEM = BAR_OFF + 512 + 1024;    // + alignment slack
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr int NCB = (TN <= 64 || HALO) ? 2 : 1;   // CORR accumulators: double buffered across tiles when they fit
-    // correction issuers: one warp for both terms (TN = 128, the tensor pipe is the limit), or one warp and one
-    // accumulator per term (TN = 64: a stage is only 192 tensor cycles, the ~75 cycles per tcgen05 instruction of an
-    // issuing thread are the limit -- so the 6 MMAs of a stage are spread over three threads)
+    // correction issuers: one warp for both terms.  (Round 1 attributed the slow issue loops to a per-instruction cost of
+    // ~75 cycles per issuing thread and tried one warp per term; tools/microbench/umma_issue.cu shows otherwise: ONE thread
+    // sustains 3 MMAs of M = N = 128 plus a commit every other stage in exactly the 192 tensor cycles -- an MMA costs its
+    // thread <= 39 cycles, a commit 9.  What slows the real loops is waiting: on operands in the per-tap kernel, on the
+    // shared-memory port in the halo variant.)
     static constexpr int NCI = 1;   // (a third issuer for TN = 64 was measured: no gain once the weight latency is the limit)
     static constexpr int THREADS = (C2_XW + 8 + 2 + 1 + NCI) * 32;
     static constexpr uint32_t A_TMEM_COL = (2 + NCB * NCI) * TN;   // ring of C2_NO stages x 32 columns behind the accumulators
