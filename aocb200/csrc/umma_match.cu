@@ -119,6 +119,7 @@ struct MatchPeers {
     const unsigned* epoch;               // device word: frames exchanged so far; parity = epoch & 1 (double-buffered slots:
                                          // a rank can run at most one frame ahead of a peer, see DESIGN)
     long long par_stride;                // floats between the parity-0 and parity-1 slots (same layout on every rank)
+    int fast;                            // 1: "fast" precision mode -- only the hi*hi term of the split product (see g_match_fast)
 };
 
 // MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test);
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                         const uint32_t b_lo = b_hi + RBK * KSTEP * 4;
                         const uint64_t dah = smem_desc(a_hi, lbo, sbo), dal = smem_desc(a_lo, lbo, sbo);
                         const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
-                        if (F16) {
+                        if (F16 && peers.fast) {
+                            mma_f16(d, dah, dbh, idesc, ks > 0 ? 1u : 0u);         // fast mode: fp16-rounded operands, one MMA
+                        } else if (F16) {
                             mma_f16(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
                             mma_f16(d, dah, dbl, idesc, 1u);
                             mma_f16(d, dah, dbh, idesc, 1u);
@@ -405,6 +408,11 @@ extern "C" int aoc_pack_tc_image_f32(const float* x, long long rows, int K, int 
 
 namespace aoc {
 int g_match_f16 = 1;     // aoc_set_option("match_f16", 0/1): split-fp16 operands in the global matching contraction
+// aoc_set_option("match_fast", 0/1): FAST precision mode of the global matching (off by default; not bit-faithful): the
+// contraction keeps only the hi*hi term of the split-fp16 product, i.e. a plain fp16 tensor-core GEMM with fp32
+// accumulation (11-bit operands, ~1e-3 absolute on the squared distances of the centred embeddings).  One third of the
+// tensor work of the exact mode; reported by bench.py --fast-match as frames/s next to IoU / argmax agreement with the oracle.
+int g_match_fast = 0;
 }
 
 static int pack_centered(const float* x, long long rows, int RB, const float* center, const float* valid_r2, void* out,
@@ -474,14 +482,16 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
             cudaFuncSetAttribute(match_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MatchFmt<true>::SMEM);
         }
         dim3 grid(nqt, nsplit);
+        MatchPeers pr0 = {};
+        pr0.fast = g_match_fast;
         if (f16)
             match_tc_kernel<0, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, 0, nrb, 0,
                                                                                  nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES,
-                                                                                 MatchPeers{});
+                                                                                 pr0);
         else
             match_tc_kernel<0, false><<<grid, 256, MatchFmt<false>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, 0, nrb, 0,
                                                                                    nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES,
-                                                                                   MatchPeers{});
+                                                                                   pr0);
         if (nsplit > 1) min_over_splits_kernel<<<cdiv(n, 256), 256, 0, stream>>>(mins, n, nsplit);
     }
     rc = aoc_global_match_finalize_f32(mins, meta_dev, bias, HW, O, out, stream);
@@ -622,6 +632,7 @@ extern "C" int aoc_global_match_tc_sharded(const float* q, int HW, const float* 
     const size_t slot = match_slot_floats(cap_hw);
     MatchPeers pr = {};
     pr.n = 0;
+    pr.fast = g_match_fast;
     for (int g = 0; g < world; ++g) {
         if (g == rank) continue;
         AOC_CHECK_ARG(areas[g], "peer area not mapped");

@@ -114,7 +114,7 @@ class ClockSampler:
                 self.mask |= int(get(self.h))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.1)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -390,6 +390,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=None, help="predicted frames timed for cpu_baseline (per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-match", action="store_true",
+                    help="FAST precision mode of the global matching (one fp16 MMA per product instead of the exact mode's three; "
+                         "not bit-faithful): the line's `parity` shows what it costs against the oracle")
     ap.add_argument("--bank-shard", action="store_true",
                     help="N > 1: ONE sequence on all N GPUs, the memory bank of the global matching sharded over the ranks "
                          "(SURVEY 8f-3; strong scaling) instead of one independent clip per GPU")
@@ -415,6 +418,10 @@ def main():
               "precision": "fp32 I/O; fp32-faithful tensor-core kernels: convolution and matching contract split-fp16 operand pairs "
                            "(22 mantissa bits, 3 kind::f16 MMAs per fp32 product), fp32 accumulate"}
 
+    if args.fast_match:
+        os.environ["AOCB200_OPTS"] = ",".join(filter(None, [os.environ.get("AOCB200_OPTS", ""), "match_fast=1"]))
+        config["precision"] += "; FAST global matching: hi*hi term only (plain fp16 operands, fp32 accumulate)"
+        config["mode"] = "fast-match"
     if args.impl == "reference":
         if rank != 0:
             return
@@ -464,7 +471,7 @@ def main():
     # contract are then taken inside each timed run
     np.random.seed(999)
     pre = Stepper(model, frames, first, K_OBJ, device, False)
-    for _ in range(min(MEM_EVERY + 1, n_frames - 1)):
+    for _ in range(n_frames - 1):          # the whole schedule once: every bank size of the timed runs has been allocated
         pre.step()
     torch.cuda.synchronize()
     del pre
