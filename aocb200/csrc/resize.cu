@@ -143,6 +143,65 @@ __global__ void resize_bicubic_kernel(const float* __restrict__ x, float* __rest
     }
 }
 
+// The decoder's only bicubic resize is an exact 2x upsampling with align_corners (61 x 107 -> 121 x 213: Ho = 2 Hi - 1), where
+// the four outputs (2i + a, 2j + b), a, b in {0, 1}, read the SAME 4 x 4 input patch (rows i-1..i+2, columns j-1..j+2).  One
+// thread computes the 2 x 2 block from one patch: 16 loads per four outputs instead of 16 per output (the general kernel
+// was bound by the L1 / LSU, 183 us for 158 MB of output); per output the arithmetic -- coefficients from the same
+// expression, the same fma order -- is that of resize_bicubic_kernel, so the results are bit-identical.
+__global__ void __launch_bounds__(256) resize_bicubic2x_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi,
+                                                               int Wi, int Ho, int Wo, int C, int ldx, int ldy, float sh, float sw) {
+    const int C4 = C >> 2;
+    const int Hb = (Ho + 1) >> 1, Wb = (Wo + 1) >> 1;                  // 2 x 2 output blocks
+    const long long total = (long long)N * Hb * Wb * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long blk = i / C4;
+        const int bj = (int)(blk % Wb);
+        const int bi = (int)((blk / Wb) % Hb);
+        const int n = (int)(blk / ((long long)Wb * Hb));
+        const size_t b = (size_t)n * Hi * Wi;
+        float4 v[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = min(max(bi - 1 + j, 0), Hi - 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int xx = min(max(bj - 1 + k, 0), Wi - 1);
+                v[j][k] = ldg4(x + (b + (size_t)yy * Wi + xx) * ldx + c);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int yo = 2 * bi + a;
+            if (yo >= Ho) continue;
+            const float ry = sh * (float)yo;                           // == bi + a / 2 exactly (sh = 0.5)
+            float wy[4];
+            cubic_coeffs(ry - floorf(ry), wy);
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int xo = 2 * bj + bb;
+                if (xo >= Wo) continue;
+                const float rx = sw * (float)xo;
+                float wx[4];
+                cubic_coeffs(rx - floorf(rx), wx);
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        r.x = fmaf(wx[k], v[j][k].x, r.x); r.y = fmaf(wx[k], v[j][k].y, r.y);
+                        r.z = fmaf(wx[k], v[j][k].z, r.z); r.w = fmaf(wx[k], v[j][k].w, r.w);
+                    }
+                    o.x = fmaf(wy[j], r.x, o.x); o.y = fmaf(wy[j], r.y, o.y);
+                    o.z = fmaf(wy[j], r.z, o.z); o.w = fmaf(wy[j], r.w, o.w);
+                }
+                *reinterpret_cast<float4*>(y + (((size_t)n * Ho + yo) * Wo + xo) * ldy + c) = o;
+            }
+        }
+    }
+}
+
 // Input edge of the eval loop (dataloaders/custom_transforms.py:387-463 MultiRestrictSize + :465-487 MultiToTensor): uint8
 // HWC frame -> cv2.resize(..., INTER_CUBIC) of the float image (A = -0.75, half-pixel centres src = (dst + 0.5) * scale - 0.5,
 // source indices clamped, horizontal pass then vertical pass) -> optional mirror (tmp[:, ::-1]) -> /255, -mean, /std ->
@@ -265,6 +324,13 @@ extern "C" int aoc_resize_bicubic_nhwc_f32(const float* x, float* y, int N, int 
     AOC_CHECK_ARG(x && y, "null pointer");
     AOC_CHECK_ARG(C % 4 == 0 && ldy % 4 == 0 && ldx % 4 == 0, "C/ld must be multiples of 4");
     long long total = (long long)N * Ho * Wo * (C / 4);
+    if (Ho == 2 * Hi - 1 && Wo == 2 * Wi - 1 && Hi > 1 && Wi > 1) {        // exact 2x: one thread per 2 x 2 output block
+        total = (long long)N * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 4);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        resize_bicubic2x_kernel<<<blocks, 256, 0, stream>>>(x, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, ac_scale(Hi, Ho), ac_scale(Wi, Wo));
+        return launch_status("aoc_resize_bicubic_nhwc_f32");
+    }
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
     resize_bicubic_kernel<<<blocks, 256, 0, stream>>>(x, y, N, Hi, Wi, Ho, Wo, C, ldx, ldy, ac_scale(Hi, Ho),

@@ -161,7 +161,11 @@ def test_resize(eng):
     want = F.interpolate(x, size=(31, 41), mode="bicubic", align_corners=True)
     out = eng.new(2, 31, 41, 256)
     eng.L.resize_bicubic_nhwc_f32(to_T(x, eng).ptr, out.ptr, 2, 16, 21, 31, 41, 256, 256, 256, eng.stream)
-    report("bicubic", from_T(out), want, 5e-6)
+    report("bicubic (exact 2x: 2 x 2 block kernel)", from_T(out), want, 5e-6)
+    want = F.interpolate(x, size=(29, 37), mode="bicubic", align_corners=True)
+    out = eng.new(2, 29, 37, 256)
+    eng.L.resize_bicubic_nhwc_f32(to_T(x, eng).ptr, out.ptr, 2, 16, 21, 29, 37, 256, 256, 256, eng.stream)
+    report("bicubic (general)", from_T(out), want, 5e-6)
     lab = torch.randint(0, 200, (1, 1, 97, 129), generator=g, dtype=torch.uint8)
     for (h, w) in ((25, 33), (13, 17), (97, 129)):
         want = F.interpolate(lab.float(), size=(h, w), mode="nearest").to(torch.uint8).view(-1)
