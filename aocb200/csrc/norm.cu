@@ -131,20 +131,32 @@ __global__ void __launch_bounds__(256) affine_stats_partial(const float* __restr
     }
 }
 
-// stats: [N][2][C] doubles
-__global__ void channel_stats_final(const double* __restrict__ part, int S, int C2, double* __restrict__ stats) {
-    int n = blockIdx.y;
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C2) return;
+// stats: [N][2][C] doubles.  Block = 32 values x 8 slab lanes: lane l adds the slabs l, l + 8, ... (two loads in flight),
+// the eight lane sums are combined in lane order -- a fixed tree, so the result does not depend on the schedule; the
+// serial chain over the slabs (101 for a 121 x 213 map) that made this tiny kernel 5-12 us long is 13 steps instead of 26 x 4.
+__global__ void __launch_bounds__(256) channel_stats_final(const double* __restrict__ part, int S, int C2,
+                                                           double* __restrict__ stats) {
+    __shared__ double sm[8][33];
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * 32 + threadIdx.x, l = threadIdx.y;
     double a = 0.0;
-    for (int s = 0; s < S; s += 4) {                     // four slabs per iteration: independent loads, added in slab order
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = s + u < S ? part[((size_t)(n * S + s + u)) * C2 + c] : 0.0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) a += v[u];
+    if (c < C2) {
+        const double* p = part + (size_t)n * S * C2 + c;
+        for (int s = l; s < S; s += 16) {
+            const double v0 = p[(size_t)s * C2];
+            const double v1 = s + 8 < S ? p[(size_t)(s + 8) * C2] : 0.0;
+            a += v0;
+            a += v1;
+        }
     }
-    stats[(size_t)n * C2 + c] = a;
+    sm[l][threadIdx.x] = a;
+    __syncthreads();
+    if (l == 0 && c < C2) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+        stats[(size_t)n * C2 + c] = t;
+    }
 }
 
 // GroupNorm coefficients: y = x*a + b with a = rstd*gamma, b = beta - mean*a   (biased variance, eps inside sqrt)
@@ -367,8 +379,8 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
         channel_stats_partial<true><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, CW, phi, thr, part);
     else
         channel_stats_partial<false><<<grid, 256, smem, stream>>>(x, HW, C, ldx, PB, CW, nullptr, nullptr, part);
-    dim3 g2(cdiv(2 * C, 256), N);
-    channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
+    dim3 g2(cdiv(2 * C, 32), N);
+    channel_stats_final<<<g2, dim3(32, 8), 0, stream>>>(part, S, 2 * C, stats);
     return launch_status("aoc_channel_stats_f32");
 }
 
@@ -391,8 +403,8 @@ extern "C" int aoc_affine_stats_nc_f32(const float* x, const float* a, const flo
     double* part = (double*)workspace;
     affine_stats_partial<<<grid, 256, smem, stream>>>(x, a, b, residual, res_scale, y, HW, C, ldx, ldy, ldres, relu, PB,
                                                       part);
-    dim3 g2(cdiv(2 * C, 256), N);
-    channel_stats_final<<<g2, 256, 0, stream>>>(part, S, 2 * C, stats);
+    dim3 g2(cdiv(2 * C, 32), N);
+    channel_stats_final<<<g2, dim3(32, 8), 0, stream>>>(part, S, 2 * C, stats);
     return launch_status("aoc_affine_stats_nc_f32");
 }
 
