@@ -304,16 +304,18 @@ __global__ void __launch_bounds__(256) gn_coeffs_tiles_kernel(const float* __res
     if (tl < lanes) {
         const int stat = it / cpg, ch = it - stat * cpg;
         const float* p = part + ((size_t)n * tiles_per_image * 2 + stat) * C + g * cpg + ch;
-        // four tiles per iteration: independent loads in flight, added in tile order
-        for (int t = tl; t < tiles_per_image; t += 4 * lanes) {
-            float v[4];
+        // sixteen rows per iteration: independent loads in flight, added in row order (the convolution writes one row per
+        // 32-pixel warp quadrant: 4 832 rows for a 121 x 213 map -- with four loads in flight the chain was 38 L2 round trips)
+        constexpr int U = 16;
+        for (int t = tl; t < tiles_per_image; t += U * lanes) {
+            float v[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int tt = t + u * lanes;
                 v[u] = tt < tiles_per_image ? __ldg(p + (size_t)tt * 2 * C) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc += (double)v[u];
+            for (int u = 0; u < U; ++u) acc += (double)v[u];
         }
     }
     sm[threadIdx.x] = acc;
