@@ -7,9 +7,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size"]
 rows = list(csv.reader(sys.stdin))
 if len(rows) >= 3:
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    print("# raw metrics (per launch):")
-    for w in WANT:
-        for i, h in enumerate(hdr):
-            if h == w:
-                print("#   %-60s %s %s" % (h, vals[i], units[i]))
+    hdr, units = rows[0], rows[1]
+    for k, vals in enumerate(rows[2:]):
+        print("# raw metrics (launch %d):" % k)
+        for w in WANT:
+            for i, h in enumerate(hdr):
+                if h == w:
+                    print("#   %-60s %s %s" % (h, vals[i], units[i]))
