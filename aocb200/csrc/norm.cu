@@ -345,9 +345,13 @@ __global__ void __launch_bounds__(256) gn_coeffs_tiles_kernel(const float* __res
     }
 }
 
-static int stats_slab(int HW) {
+// pixels per slab (= per block) of the statistics kernels: 256, halved down to 32 while the launch has fewer than four
+// blocks per SM (N = 1 maps of the backbone: the global average pool over 31 x 54 x 2048 ran on 14 blocks, 77 us for 14 MB)
+static int stats_slab(int N, int HW, int C) {
     int pb = 256;
     while ((long long)cdiv(HW, pb) > 1024) pb *= 2;
+    const long long z = cdiv(C, 1024);
+    while (pb > 32 && (long long)cdiv(HW, pb) * N * z < 4 * 148) pb /= 2;
     return pb;
 }
 
@@ -356,7 +360,7 @@ static int stats_slab(int HW) {
 using namespace aoc;
 
 extern "C" size_t aoc_channel_stats_workspace_bytes(int N, int HW, int C) {
-    int PB = stats_slab(HW);
+    int PB = stats_slab(N, HW, C);
     size_t S = (size_t)cdiv(HW, PB);
     return (size_t)N * S * 2 * C * sizeof(double);
 }
@@ -370,7 +374,7 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
     AOC_CHECK_ARG((((uintptr_t)x) & 15) == 0, "x must be 16-byte aligned");
     AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
     AOC_CHECK_ARG((phi == nullptr) == (thr == nullptr), "phi and thr go together");
-    int PB = stats_slab(HW);
+    int PB = stats_slab(N, HW, C);
     int S = cdiv(HW, PB);
     int CW = C < 1024 ? C : 1024;
     int PL = 256 / (CW / 4);
@@ -397,7 +401,7 @@ extern "C" int aoc_affine_stats_nc_f32(const float* x, const float* a, const flo
                   "C (<= 1024) and the row strides must be multiples of 4");
     AOC_CHECK_ARG(((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0, "pointers must be 16-byte aligned");
     AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
-    int PB = stats_slab(HW);
+    int PB = stats_slab(N, HW, C);
     int S = cdiv(HW, PB);
     int PL = 256 / (C / 4);
     size_t smem = (size_t)PL * 2 * C * sizeof(float);
