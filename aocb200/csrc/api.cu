@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace aoc
 
-namespace aoc { extern int g_conv_chunk; extern int g_conv_dbg; extern int g_conv_splitk; extern int g_conv_narrow_nit; extern int g_conv_pdl; extern int g_match_f16; extern int g_conv_halo; extern int g_match_fast; }
+namespace aoc { extern int g_conv_chunk; extern int g_conv_dbg; extern int g_conv_splitk; extern int g_conv_narrow_nit; extern int g_conv_pdl; extern int g_match_f16; extern int g_conv_halo; extern int g_match_fast; extern int g_conv_tail; extern int g_conv_tail_min_stages; }
 
 extern "C" int aoc_version(void) { return 200; }
 
@@ -25,6 +25,8 @@ extern "C" int aoc_set_option(const char* key, int value) {
     if (key && !strcmp(key, "conv_splitk")) { aoc::g_conv_splitk = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "match_fast")) { aoc::g_match_fast = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "match_f16")) { aoc::g_match_f16 = value != 0; return AOC_OK; }
+    if (key && !strcmp(key, "conv_tail_min_stages") && value >= 0) { aoc::g_conv_tail_min_stages = value; return AOC_OK; }
+    if (key && !strcmp(key, "conv_tail")) { aoc::g_conv_tail = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_halo")) { aoc::g_conv_halo = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_pdl")) { aoc::g_conv_pdl = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_narrow_nit") && value >= 0) { aoc::g_conv_narrow_nit = value; return AOC_OK; }

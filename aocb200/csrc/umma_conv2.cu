@@ -75,6 +75,7 @@ struct Conv2P {
     int ncc, nIt, chunk, taps;
     int tiles_n, total_tiles;
     int ksplit;             // split-K factor: work item = (tile, K slice); slices write raw partial sums to `ws`
+    int tail_mode, n_plain; // tail splitting (see decode): items below n_plain are whole tiles, the rest K slices of the tail tiles
     float* ws;              // [ksplit][N*Ho*Wo][Cout] partial sums (ksplit > 1)
     int* ws_cnt;            // [total_tiles] arrival counters of the K slices (zero between launches)
     unsigned long long* trace;   // tooling only (aoc_conv_trace): clock64 of pipeline events of CTA 0, [event < 16][stage < 256]
@@ -184,9 +185,11 @@ struct C2Cfg {
 // (tile, K slice): the slice covers the raw stages [r0, r1) of the (tap, 32-channel box) sequence, i.e. the operand
 // stages [it0, it1).  Without it the K fields are the whole range and fold away (the issue loops of the plain kernel must
 // not carry them: a Tile kept in local memory cost 18 % on the large layers).
-struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0; };
+struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0, tile, nsl; };   // tile: flat tile index; nsl: K slices of it
 
-template <int TN, bool SK, bool F16, bool HALO = false>
+// SK: 0 = every work item is a whole tile, 1 = split-K of every tile (small maps), 2 = tail splitting (K slices for the tiles
+// of the partial last wave only)
+template <int TN, int SK, bool F16, bool HALO = false>
 __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel(const __grid_constant__ CUtensorMap tmapA, Conv2P p) {
     static_assert(!HALO || (F16 && !SK && C2_NS == 2), "the halo variant is split-fp16, unsplit, two transform warpgroups");
     using Cfg = C2Cfg<TN, F16, HALO>;
@@ -231,16 +234,25 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
     // channel tile fastest, so CTAs running side by side share the activation patch in L2.  Every role walks the same
     // tile sequence and the rings keep flowing across tile boundaries (the producers run ahead into the next tile).
     const int nrc = (p.ncc + 1) >> 1;                        // raw (32-channel) stages per tap
-    const int n_items = SK ? p.total_tiles * p.ksplit : p.total_tiles;
+    const int n_items = SK == 1 ? p.total_tiles * p.ksplit : SK == 2 ? p.n_plain + (p.total_tiles - p.n_plain) * p.ksplit : p.total_tiles;
     auto decode = [&](int w) {
         Tile tl;
         int t = w;
         if (SK) {
-            t = w / p.ksplit;
-            tl.ks = w - t * p.ksplit;
+            int nsl = p.ksplit;
+            if (SK == 2) {
+                // tail splitting: the whole waves of tiles run unsplit, the tiles of the last, partial wave are cut into
+                // `ksplit` K slices each so that the wave fills the chip (items n_plain .. : tile-major, slice fastest)
+                if (w < p.n_plain) { t = w; tl.ks = 0; nsl = 1; }
+                else { const int u = w - p.n_plain; t = p.n_plain + u / p.ksplit; tl.ks = u - (t - p.n_plain) * p.ksplit; }
+            } else {
+                t = w / p.ksplit;
+                tl.ks = w - t * p.ksplit;
+            }
+            tl.nsl = nsl;
             const int R = p.taps * nrc;
-            tl.r0 = R * tl.ks / p.ksplit;
-            tl.r1 = R * (tl.ks + 1) / p.ksplit;
+            tl.r0 = R * tl.ks / nsl;
+            tl.r1 = R * (tl.ks + 1) / nsl;
             int tp = tl.r0 / nrc;
             tl.tap0 = tp;
             tl.cc0 = 2 * (tl.r0 - tp * nrc);
@@ -248,8 +260,9 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             tp = tl.r1 / nrc;
             tl.it1 = tp * p.ncc + min(2 * (tl.r1 - tp * nrc), p.ncc);
         } else {
-            tl.ks = 0; tl.r0 = 0; tl.r1 = p.taps * nrc; tl.tap0 = 0; tl.cc0 = 0; tl.it0 = 0; tl.it1 = nIt;
+            tl.ks = 0; tl.r0 = 0; tl.r1 = p.taps * nrc; tl.tap0 = 0; tl.cc0 = 0; tl.it0 = 0; tl.it1 = nIt; tl.nsl = 1;
         }
+        tl.tile = t;
         const int mt = t / p.tiles_n;
         tl.n0 = (t - mt * p.tiles_n) * TN;
         tl.n = mt / tpi;
@@ -608,6 +621,42 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             __syncwarp();
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
             if (threadIdx.x == C2_XT) C2_TRACE(13, tl.it0);
+            if (SK == 2 && tl.nsl > 1) {
+                // ---- tail splitting: slices 1.. park their partial accumulators (this thread's row, its NC channels) in the
+                // workspace and move on; slice 0 waits for them, adds them in slice order (deterministic) and runs the normal
+                // epilogue -- bias, residual, ReLU, statistics, all as for an unsplit tile.  Slices never wait for slice 0 and all
+                // slices of the tail are in one wave (launcher), so nothing can block.
+                const int tt = tl.tile - p.n_plain;
+                int* cnt = p.ws_cnt + tt;
+                float* mine = p.ws + ((size_t)tt * (tl.nsl - 1)) * (C2_BM * TN) + (size_t)(q * 32 + lane) * TN + half * NC;
+                if (tl.ks > 0) {
+                    float* dst = mine + (size_t)(tl.ks - 1) * (C2_BM * TN);
+#pragma unroll
+                    for (int c = 0; c < NC; c += 4)
+                        __stcg(reinterpret_cast<float4*>(dst + c), make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+                    __threadfence();
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (threadIdx.x == C2_XT) atomicAdd(cnt, 1);
+                    continue;                                        // no epilogue for this slice
+                }
+                if (threadIdx.x == C2_XT) {
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                    } while (v < tl.nsl - 1);
+                    *cnt = 0;                                        // ready for the next launch (every slice has arrived)
+                    __threadfence();
+                }
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                for (int sl = 0; sl < tl.nsl - 1; ++sl) {
+                    const float* src = mine + (size_t)sl * (C2_BM * TN);
+#pragma unroll
+                    for (int c = 0; c < NC; c += 4) {
+                        const float4 v4 = __ldcg(reinterpret_cast<const float4*>(src + c));
+                        acc[c] += v4.x; acc[c + 1] += v4.y; acc[c + 2] += v4.z; acc[c + 3] += v4.w;
+                    }
+                }
+            }
             if (NCB == 2) cb ^= 1;
             // ---- epilogue.  The accumulators sit one pixel row per thread; stored that way every warp store would touch 32
             // different lines (and the residual loads likewise).  Each warp therefore transposes 32 pixels x 32 channels
@@ -618,7 +667,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             // acc[0..31]): the unrolled version was 3 000 instructions per kernel, and on the short-K layers -- where the
             // epilogue is the critical path -- a third of the drain warps' stalls were instruction-cache misses.
             const int cbase = tl.n0 + half * NC;
-            const bool partial = SK;                                 // split-K: raw partial sums of this K slice to `ws`
+            constexpr bool partial = SK == 1;                        // split-K: raw partial sums of this K slice to `ws`
             float* const ybase = partial ? p.ws + (size_t)tl.ks * ((size_t)p.N * p.Ho * p.Wo) * p.Cout : p.y;
             const int ldo = partial ? p.Cout : p.ldy;
             const float* const bias = partial ? nullptr : p.bias;
@@ -626,7 +675,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             const bool relu = !partial && p.relu;
             const int r_sub = lane >> 3, ch4 = lane & 7;
             // statistics row of this warp: (pixel tile, 32-pixel quadrant) -- no cross-warp step, no block barrier
-            float* const strow = (!SK && p.tile_stats) ? p.tile_stats + (size_t)((t / p.tiles_n) * 4 + q) * 2 * p.Cout : nullptr;
+            float* const strow = (!partial && p.tile_stats) ? p.tile_stats + (size_t)((tl.tile / p.tiles_n) * 4 + q) * 2 * p.Cout : nullptr;
             int pixi[8], rowoff[8];                                  // output pixel of row i * 4 + r_sub (-1: outside), its offset in y
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -738,7 +787,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                 }
             }
             if (threadIdx.x == C2_XT) C2_TRACE(14, tl.it0);
-            if (SK) {
+            if (partial) {
                 // ---- split-K finish, fused (the separate finish kernel -- 65 launches per frame on the 31x54 backbone maps --
                 // is gone).  Every K slice of a tile runs on its own CTA at the same time (the launcher splits only when
                 // tiles x slices <= SMs, one work item per CTA), so the slices MEET at the tile's counter: each writes its
@@ -746,7 +795,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                 // tile's 128 pixel rows -- the partial tiles are added in slice order (deterministic), bias / residual /
                 // ReLU applied, y written.  The other slices' sums are read with ld.global.cg (written by other SMs during
                 // this launch).  A second round of arrivals tells the last slice to clear the counter for the next launch.
-                int* cnt = p.ws_cnt + t / p.ksplit;
+                int* cnt = p.ws_cnt + tl.tile;
                 __threadfence();
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (threadIdx.x == C2_XT) {
@@ -1190,6 +1239,8 @@ static EncodeTiledFn get_encode() {
 
 constexpr size_t C2_WS_HEADER = 4096;   // split-K arrival counters (one int per output tile) in front of the partial sums
 int g_conv_splitk = 1;   // aoc_set_option("conv_splitk", 0/1)
+int g_conv_tail = 1;     // aoc_set_option("conv_tail", 0/1): K-split of the tiles of a partial last wave (tail splitting)
+int g_conv_tail_min_stages = 192;   // aoc_set_option("conv_tail_min_stages", n): shortest K loop (16-channel stages) it is used for
 int g_conv_pdl = 1;      // aoc_set_option("conv_pdl", 0/1): programmatic dependent launch of the convolution kernels
 int g_conv_narrow_nit = 0;    // aoc_set_option("conv_narrow_nit", stages): 64-wide tiles for K loops shorter than this (measured: never better)
 
@@ -1198,8 +1249,9 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
                         cudaStream_t stream) {
     static PerDeviceOnce attr;
     if (attr.first()) {
-        cudaFuncSetAttribute(conv2_kernel<TN, false, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
-        cudaFuncSetAttribute(conv2_kernel<TN, true, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, 0, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, 1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, 2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2Cfg<TN, F16>::SMEM);
     }
     Conv2P q = p;
     q.tiles_n = cdiv(p.Cout, TN);
@@ -1222,7 +1274,26 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
         while (S > 1 && hdr + (size_t)S * M * p.Cout * sizeof(float) > ws_bytes) --S;
         if (S > 1) { q.ksplit = S; q.ws = (float*)((char*)workspace + hdr); q.ws_cnt = (int*)workspace; }
     }
-    const int items = q.total_tiles * q.ksplit;
+    // tail splitting: with T tiles on G persistent CTAs the last wave holds T mod G tiles (336 tiles of a 61 x 107 x 6 layer:
+    // two full waves and 40 tiles -- a third of the launch spent at 27 % occupancy).  Those tail tiles are cut into S K slices
+    // each, S * tail <= G, so that the last wave fills the chip and lasts 1 / S of a tile (+ the hand-over: slices 1.. park their
+    // accumulators in the workspace, slice 0 adds them in order and runs the normal epilogue, statistics included).
+    q.tail_mode = 0; q.n_plain = 0;
+    // (the hand-over costs ~10 us -- park, fence, spin, add -- so it only pays for long K loops: measured +16 us on a 32-stage
+    // 1x1 layer, -20 us on the 288-stage dilated ASPP convolutions)
+    if (g_conv_tail && q.ksplit == 1 && q.total_tiles > sms && p.nIt >= g_conv_tail_min_stages && workspace &&
+        ws_bytes >= C2_WS_HEADER) {
+        const int tail = q.total_tiles % sms;
+        int S = tail > 0 ? sms / tail : 0;
+        if (S > C2_MAX_KSPLIT) S = C2_MAX_KSPLIT;
+        if (S > R / 4) S = R / 4;                                     // >= 4 raw stages (8 operand stages) per slice
+        while (S > 1 && C2_WS_HEADER + (size_t)tail * (S - 1) * C2_BM * TN * sizeof(float) > ws_bytes) --S;
+        if (S > 1 && (size_t)tail * sizeof(int) <= C2_WS_HEADER) {
+            q.tail_mode = 1; q.n_plain = q.total_tiles - tail; q.ksplit = S;
+            q.ws = (float*)((char*)workspace + C2_WS_HEADER); q.ws_cnt = (int*)workspace;
+        }
+    }
+    const int items = q.tail_mode ? q.n_plain + (q.total_tiles - q.n_plain) * q.ksplit : q.total_tiles * q.ksplit;
     const int grid = items < sms ? items : sms;                       // persistent: one CTA per SM walks the work list
     cudaLaunchAttribute attr_pdl[1];
     attr_pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1230,10 +1301,12 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C2Cfg<TN, F16>::THREADS); cfg.dynamicSmemBytes = C2Cfg<TN, F16>::SMEM;
     cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
-    if (q.ksplit > 1) {
-        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, true, F16>, map, q);
+    if (q.tail_mode) {
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, 2, F16>, map, q);
+    } else if (q.ksplit > 1) {
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, 1, F16>, map, q);
     } else {
-        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false, F16>, map, q);
+        cudaLaunchKernelEx(&cfg, conv2_kernel<TN, 0, F16>, map, q);
     }
     return launch_status("aoc_conv2d_nhwc_tc");
 }
@@ -1245,7 +1318,7 @@ static int launch_conv2_halo(const CUtensorMap& map, const Conv2P& p, int tiles,
     static_assert(Cfg::SMEM <= 232448, "shared memory of the halo variant");
     static PerDeviceOnce attr;
     if (attr.first())
-        cudaFuncSetAttribute(conv2_kernel<TN, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        cudaFuncSetAttribute(conv2_kernel<TN, 0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     Conv2P q = p;
     q.tiles_n = cdiv(p.Cout, TN);
     q.total_tiles = tiles * q.tiles_n;
@@ -1258,7 +1331,7 @@ static int launch_conv2_halo(const CUtensorMap& map, const Conv2P& p, int tiles,
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = stream; cfg.attrs = attr_pdl; cfg.numAttrs = g_conv_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, conv2_kernel<TN, false, true, true>, map, q);
+    cudaLaunchKernelEx(&cfg, conv2_kernel<TN, 0, true, true>, map, q);
     return launch_status("aoc_conv2d_nhwc_tc (halo)");
 }
 
@@ -1325,7 +1398,12 @@ extern "C" size_t aoc_conv_workspace_bytes(int N, int H, int W, int Cout, int kh
     int gH, gW, Ho, Wo, l2;
     conv_geometry(H, W, kh, kw, stride, pad, dil, &gH, &gW, &Ho, &Wo, &l2);
     if (Ho <= 0 || Wo <= 0) return 0;
-    return C2_WS_HEADER + (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
+    // split-K of a small map: up to C2_MAX_KSPLIT partial images; tail splitting of a large one: at most one parked
+    // accumulator tile (128 x 128 floats) per SM
+    const size_t full = (size_t)C2_MAX_KSPLIT * N * Ho * Wo * Cout * sizeof(float);
+    const size_t tail = (size_t)device_sms() * C2_BM * 128 * sizeof(float);
+    const long long M = (long long)N * Ho * Wo;
+    return C2_WS_HEADER + (M <= 128 * 74 ? (full > tail ? full : tail) : tail);
 }
 
 extern "C" int aoc_conv_trace(void* device_buffer_16x256_u64) {

@@ -300,10 +300,10 @@ class Engine:
             if stats:
                 tpi = self.L.conv_tiles_per_image(x.N, x.H, x.W, Cin, Cout, kh, kw, stride, pad, dil, mode)
                 ts = self.empty(x.N * tpi * 2 * Cout)
-            wsp, wsn = None, 0
-            if x.N * Ho * Wo <= 128 * 74 and not stats:       # few pixel tiles: let the library split K
-                wsn = self.L.conv_workspace_bytes(x.N, x.H, x.W, Cout, kh, kw, stride, pad, dil)
-                wsp = self.ws("conv_splitk", wsn, zero_head=4096).data_ptr()
+            # scratch for the library's K splits: whole-layer split-K of the small maps (few pixel tiles) and tail splitting of
+            # a partial last wave (one parked accumulator tile per SM); its 4 KB header of arrival counters stays zero
+            wsn = self.L.conv_workspace_bytes(x.N, x.H, x.W, Cout, kh, kw, stride, pad, dil)
+            wsp = self.ws("conv_splitk", wsn, zero_head=4096).data_ptr()
             self.L.conv2d_nhwc_tc(x.ptr, wp[1].data_ptr(), _p(b), None if res is None else res.ptr, _p(in_scale),
                                   _p(in_shift), 1 if in_relu else 0, out.ptr, _p(ts), x.N, x.H, x.W, Cin, x.ld, Cout,
                                   out.ld, 0 if res is None else res.ld, kh, kw, stride, pad, dil, 1 if relu else 0,

@@ -232,3 +232,51 @@ def test_conv_tc_halo_variant(eng):
         finally:
             L.set_option(b"conv_halo", 1)
         print("[parity]    halo %.3e   per-tap %.3e   cpu fp32 %.3e" % (e_h, e_t, e32))
+
+
+def test_conv_tc_tail_split(eng):
+    """Tail splitting (the tiles of a partial last wave are cut into K slices; slice 0 collects the parked accumulators and
+    runs the normal epilogue): results against float64 and against the unsplit schedule, and the epilogue statistics rows
+    (per-channel sum / sum of squares) against the unsplit schedule -- on the two layer types it serves in the 480p frame."""
+    eng.tc_conv = True
+    L = eng.L
+    c = _conv_tc_case
+    L.set_option(b"conv_tail_min_stages", 0)               # the launcher only takes it for K loops of >= 192 stages: test it on all
+    try:
+        _tail_split_cases(eng, L, c)
+    finally:
+        L.set_option(b"conv_tail_min_stages", 192)
+
+
+def _tail_split_cases(eng, L, c):
+    for kw in (dict(N=6, H=61, W=107, Cin=512, Cout=128, k=1, pad=0, dil=1, seed=301, scale=True, shift=True, in_relu=True, bias=False),
+               dict(N=6, H=61, W=107, Cin=128, Cout=128, k=3, pad=12, dil=12, seed=302, scale=True, bias=False),
+               dict(N=1, H=121, W=213, Cin=256, Cout=64, k=1, pad=0, dil=1, seed=303, relu=True, res=True)):
+        kw = dict(kw)
+        N, H, W, Cin, Cout, k, pad, dil = (kw.pop(x) for x in ("N", "H", "W", "Cin", "Cout", "k", "pad", "dil"))
+        L.set_option(b"conv_tail", 1)
+        e_t, e32 = c(eng, N, H, W, Cin, Cout, k, 1, pad, dil, **kw)
+        L.set_option(b"conv_tail", 0)
+        try:
+            e_u, _ = c(eng, N, H, W, Cin, Cout, k, 1, pad, dil, **kw)
+        finally:
+            L.set_option(b"conv_tail", 1)
+        print("[parity]    tail-split %.3e   unsplit %.3e   cpu fp32 %.3e" % (e_t, e_u, e32))
+    # statistics rows through the engine's own path
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(6, 128, 61, 107, generator=g)
+    w = torch.randn(128, 128, 3, 3, generator=g) / (128 * 9) ** 0.5
+    eng.w.conv["tc.tail"] = (w.permute(0, 2, 3, 1).contiguous().cuda(), None, (128, 3, 3, 128))
+    xt = to_T(x, eng)
+    res = []
+    for on in (1, 0):
+        L.set_option(b"conv_tail", on)
+        y, st = eng.conv(xt, "tc.tail", pad=6, dil=6, stats=True)
+        res.append((from_T(y).clone(), eng.dense_stats(st).clone().cpu()))
+    L.set_option(b"conv_tail", 1)
+    dy = (res[0][0] - res[1][0]).abs().max().item()
+    ds = ((res[0][1] - res[1][1]).abs() / (res[1][1].abs() + 1.0)).max().item()
+    want = torch.stack([from_T(res[1][0] if False else y).double().sum((2, 3)), (from_T(y).double() ** 2).sum((2, 3))], 1).reshape(-1)
+    dw = ((res[0][1] - want).abs() / (want.abs() + 1.0)).max().item()
+    print("[parity] tail-split vs unsplit: outputs %.3e, statistics (relative) %.3e; statistics vs recomputed %.3e" % (dy, ds, dw))
+    assert dy < 5e-6 and ds < 1e-5 and dw < 1e-5
