@@ -138,16 +138,16 @@ __device__ __forceinline__ void fmul2(float& x0, float& x1, float c) {
 // the MAIN issuer's iteration -- barrier waits (~100 cycles per try_wait, not overlappable), tcgen05 fence, elect, the
 // uniform-register chain in front of each tcgen05 instruction, on a sub-partition shared with four busy warps -- took
 // ~385 cycles per stage, hence one full barrier per PAIR of stages for both operands and two stages per iteration.
-// Halo variant (3x3, stride 1, pad = dilation = 1, split-fp16): output tiles of 16 rows x 8 columns; the raw halo patch
-// (18 x 10 pixels x 32 channels) of a channel box is loaded ONCE (not once per filter tap), transformed ONCE into
+// Halo variant (3x3, stride 1, pad = dilation <= 2, split-fp16): output tiles of 16 rows x 8 columns; the raw halo patch
+// (18 x 10 pixels x 32 channels; 20 x 12 for dilation 2) of a channel box is loaded ONCE (not once per filter tap), transformed ONCE into
 // split-fp16 operand tiles in SHARED memory, and the nine taps of the box read that tile through nine descriptor start
 // addresses: K-major SWIZZLE_NONE core matrices = 8 consecutive pixels of a halo row x 8 channels (16 B per pixel), the
 // 8-row-group stride (SBO) is one halo row, the k-group stride (LBO) one pixel plane.
 constexpr int C2H_TH = 16, C2H_TW = 8;                           // output tile (rows x columns) = 128 pixels
-constexpr int C2H_D = 1;                                         // dilation (= padding) the shared-memory budget is sized for
+constexpr int C2H_D = 2;                                         // largest dilation (= padding) the shared-memory budget is sized for
 constexpr int C2H_P = (C2H_TH + 2 * C2H_D) * (C2H_TW + 2 * C2H_D);      // halo pixels (180)
 constexpr uint32_t C2H_RAW_BYTES = (C2H_P * 128 + 1023) / 1024 * 1024;  // raw halo box: P rows of 32 fp32, 1 KB aligned (swizzle)
-constexpr int C2H_NRAW = 3;                                      // raw halo ring depth
+constexpr int C2H_NRAW = 2;                                      // raw halo ring depth (a box lasts 18 stages: one in use, one in flight)
 constexpr uint32_t C2H_A_HALF = 4 * C2H_P * 16;                  // hi (or lo) operand tile of a box: 4 k-groups x P pixels x 16 B
 constexpr uint32_t C2H_A_BUF = 2 * C2H_A_HALF;                   // hi + lo
 

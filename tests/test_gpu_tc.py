@@ -221,14 +221,16 @@ def test_conv_tc_halo_variant(eng):
              dict(N=6, H=61, W=107, Cin=64, Cout=64, seed=202, scale=True, shift=True, in_relu=True, bias=False),
              dict(N=1, H=121, W=213, Cin=128, Cout=256, seed=203, res=True, relu=True),
              dict(N=4, H=50, W=75, Cin=320, Cout=128, seed=204, bias=False)]
+    cases.append(dict(N=6, H=61, W=107, Cin=128, Cout=128, seed=205, d=2, scale=True, shift=True, in_relu=True, bias=False))   # dilation 2
     for kw in cases:
         kw = dict(kw)
         N, H, W, Cin, Cout = (kw.pop(k) for k in ("N", "H", "W", "Cin", "Cout"))
-        assert L.conv_tiles_per_image(N, H, W, Cin, Cout, 3, 3, 1, 1, 1, 1) == 4 * ((W + 7) // 8) * ((H + 15) // 16), "halo not selected"
-        e_h, e32 = c(eng, N, H, W, Cin, Cout, 3, 1, 1, 1, **kw)
+        d = kw.pop("d", 1)
+        assert L.conv_tiles_per_image(N, H, W, Cin, Cout, 3, 3, 1, d, d, 1) == 4 * ((W + 7) // 8) * ((H + 15) // 16), "halo not selected"
+        e_h, e32 = c(eng, N, H, W, Cin, Cout, 3, 1, d, d, **kw)
         L.set_option(b"conv_halo", 0)
         try:
-            e_t, _ = c(eng, N, H, W, Cin, Cout, 3, 1, 1, 1, **kw)
+            e_t, _ = c(eng, N, H, W, Cin, Cout, 3, 1, d, d, **kw)
         finally:
             L.set_option(b"conv_halo", 1)
         print("[parity]    halo %.3e   per-tap %.3e   cpu fp32 %.3e" % (e_h, e_t, e32))
