@@ -52,7 +52,7 @@ int aoc_check_device(int dev);
  * length, in 16-channel stages, of the TMEM accumulation chains of the tensor-core convolution (see
  * aoc_conv2d_nhwc_tc).  "conv_splitk" (default 1): allow the split-K schedule for layers with few output tiles.
  * "conv_pdl" (default 1): programmatic dependent launch.  "match_f16" (default 1): split-fp16 operands in the matching
- * contraction (0 = 3xTF32).  "conv_halo" (default 1): halo variant of the convolution for 3x3 / stride-1 / pad = dilation = 1
+ * contraction (0 = 3xTF32).  "conv_halo" (default 1): halo variant of the convolution for 3x3 / stride-1 / pad = dilation <= 2
  * layers with at least one 16 x 8 tile per SM.  "conv_tail" (default 1) / "conv_tail_min_stages" (default 192): K slices
  * for the tiles of a partial last wave of long K loops.  "match_fast" (default 0): FAST precision mode of the global matching
  * -- one fp16 MMA per product instead of three; the only switch that changes results beyond fp32 rounding (schedules differ in
