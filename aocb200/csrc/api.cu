@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace aoc
 
-namespace aoc { extern int g_conv_chunk; extern int g_conv_dbg; extern int g_conv_splitk; extern int g_conv_narrow_nit; extern int g_conv_pdl; extern int g_match_f16; extern int g_conv_halo; extern int g_match_fast; extern int g_conv_tail; extern int g_conv_tail_min_stages; }
+namespace aoc { extern int g_conv_chunk; extern int g_conv_dbg; extern int g_conv_splitk; extern int g_conv_narrow_nit; extern int g_conv_pdl; extern int g_match_f16; extern int g_conv_halo; extern int g_match_fast; extern int g_match_collector; extern int g_conv_tail; extern int g_conv_tail_min_stages; }
 
 extern "C" int aoc_version(void) { return 200; }
 
@@ -24,6 +24,7 @@ extern "C" int aoc_set_option(const char* key, int value) {
     if (key && !strcmp(key, "conv_dbg") && value >= 0) { aoc::g_conv_dbg = value; return AOC_OK; }
     if (key && !strcmp(key, "conv_splitk")) { aoc::g_conv_splitk = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "match_fast")) { aoc::g_match_fast = value != 0; return AOC_OK; }
+    if (key && !strcmp(key, "match_collector")) { aoc::g_match_collector = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "match_f16")) { aoc::g_match_f16 = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_tail_min_stages") && value >= 0) { aoc::g_conv_tail_min_stages = value; return AOC_OK; }
     if (key && !strcmp(key, "conv_tail")) { aoc::g_conv_tail = value != 0; return AOC_OK; }

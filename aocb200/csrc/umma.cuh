@@ -127,6 +127,30 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with a collector hint for the A operand: FILL keeps A in the tensor core's collector buffer after this MMA,
+// LASTUSE takes A from the buffer (the previous MMA of this thread filled it with the same matrix) instead of re-reading
+// it from shared memory -- two consecutive products with the same A (hi * lo' after hi * hi') fetch it once
+// (measured in the matching kernel: 12 % SLOWER than three plain MMAs, see g_match_collector; kept for experiments)
+__device__ __forceinline__ void mma_f16_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_alast(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 rows = TMEM lanes, one 32-bit column per k element) is read from
 // tensor memory, which leaves the shared-memory port to the B operand and the TMA writes
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

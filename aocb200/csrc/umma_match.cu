@@ -120,6 +120,7 @@ struct MatchPeers {
                                          // a rank can run at most one frame ahead of a peer, see DESIGN)
     long long par_stride;                // floats between the parity-0 and parity-1 slots (same layout on every rank)
     int fast;                            // 1: "fast" precision mode -- only the hi*hi term of the split product (see g_match_fast)
+    int collector;                       // 1: hi(A) is kept in the tensor core's collector between the two products it is in
 };
 
 // MODE 0: matching epilogue (running min per object -> mins[split][HW][O]);  MODE 1: raw C = A*B^T (self-test);
@@ -219,6 +220,10 @@ __global__ void __launch_bounds__(256, 1) match_tc_kernel(const uint8_t* __restr
                         const uint64_t dbh = smem_desc(b_hi, lbo, sbo), dbl = smem_desc(b_lo, lbo, sbo);
                         if (F16 && peers.fast) {
                             mma_f16(d, dah, dbh, idesc, ks > 0 ? 1u : 0u);         // fast mode: fp16-rounded operands, one MMA
+                        } else if (F16 && peers.collector) {
+                            mma_f16(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                            mma_f16_afill(d, dah, dbl, idesc, 1u);             // hi(A) fetched once for the two products it is in
+                            mma_f16_alast(d, dah, dbh, idesc, 1u);
                         } else if (F16) {
                             mma_f16(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
                             mma_f16(d, dah, dbl, idesc, 1u);
@@ -413,6 +418,11 @@ int g_match_f16 = 1;     // aoc_set_option("match_f16", 0/1): split-fp16 operand
 // accumulation (11-bit operands, ~1e-3 absolute on the squared distances of the centred embeddings).  One third of the
 // tensor work of the exact mode; reported by bench.py --fast-match as frames/s next to IoU / argmax agreement with the oracle.
 int g_match_fast = 0;
+// aoc_set_option("match_collector", 0/1): collector hints on the A operand of the split product (same arithmetic, same
+// order: hi(A) is fetched from shared memory once for the two products it is in -- UTCHMMA ... .A_REUSE in the SASS).
+// Measured on B200 (bench.py, three runs on one box): 358 TFLOP/s fp32-equivalent without the hints, 316-317 with them --
+// a kept collector serialises the two MMAs behind each other's operand fetch instead of saving one; off by default.
+int g_match_collector = 0;
 }
 
 static int pack_centered(const float* x, long long rows, int RB, const float* center, const float* valid_r2, void* out,
@@ -484,6 +494,7 @@ extern "C" int aoc_global_match_tc(const float* q, int HW, const float* S, const
         dim3 grid(nqt, nsplit);
         MatchPeers pr0 = {};
         pr0.fast = g_match_fast;
+        pr0.collector = g_match_collector;
         if (f16)
             match_tc_kernel<0, true><<<grid, 256, MatchFmt<true>::SMEM, stream>>>(Qimg, Simg, q2, r2c, meta_dev, O, HW, 0, nrb, 0,
                                                                                  nsplit, mins, nullptr, 0, LBO_BYTES, SBO_BYTES,
@@ -633,6 +644,7 @@ extern "C" int aoc_global_match_tc_sharded(const float* q, int HW, const float* 
     MatchPeers pr = {};
     pr.n = 0;
     pr.fast = g_match_fast;
+    pr.collector = g_match_collector;
     for (int g = 0; g < world; ++g) {
         if (g == rank) continue;
         AOC_CHECK_ARG(areas[g], "peer area not mapped");

@@ -56,7 +56,8 @@ int aoc_check_device(int dev);
  * layers with at least one 16 x 8 tile per SM.  "conv_tail" (default 1) / "conv_tail_min_stages" (default 192): K slices
  * for the tiles of a partial last wave of long K loops.  "match_fast" (default 0): FAST precision mode of the global matching
  * -- one fp16 MMA per product instead of three; the only switch that changes results beyond fp32 rounding (schedules differ in
- * summation order only), off unless a caller asks for it. */
+ * summation order only), off unless a caller asks for it.  "match_collector" (default 0): tcgen05 collector hints on the
+ * query operand of the matching contraction (identical results; measured slower, kept as an experiment switch). */
 int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */

@@ -78,7 +78,7 @@ def main():
         fl = 2.0 * N * out.H * out.W * Cout * k * k * Cin
         by = 4.0 * (N * H * W * Cin + N * out.H * out.W * Cout)
         tot += us
-        print("%-40s %9.1f us  %7.1f TFLOP/s (fp32-equivalent; x3 TF32 issued)  %7.1f GB/s in+out" %
+        print("%-40s %9.1f us  %7.1f TFLOP/s (fp32-equivalent; 3 split-fp16 MMAs issued per product)  %7.1f GB/s in+out" %
               (name, us, fl / us / 1e6, by / us / 1e3))
     print("total %.1f us" % tot)
 
