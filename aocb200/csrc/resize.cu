@@ -14,6 +14,25 @@ __global__ void nchw3_to_nhwc4_kernel(const float* __restrict__ x, float* __rest
     *reinterpret_cast<float4*>(y + (size_t)p * 4) = v;
 }
 
+// image [3,H,W] -> space-to-depth image [H2 + 1][W2 + 1][16], H2 = ceil(H / 2): pixel (i, j) holds the 2 x 2 block of source
+// pixels (2 (i - 1) + py, 2 (j - 1) + px) as channels (py * 2 + px) * 4 + c (c = 3 and everything outside the image: zero;
+// row 0 and column 0 are zero).  A 7 x 7 / stride-2 / pad-3 convolution over the image is a 4 x 4 / stride-1 / pad-1
+// convolution over this tensor (tap a' of the 4 covers source taps r = 2 a' + py - 1): the stem runs 16 stages of 16 real
+// channels instead of 49 stages of 4 real + 12 zero channels.
+__global__ void image_to_s2d16_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int H2p, int W2p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (output pixel, quarter = source pixel of the block)
+    if (idx >= H2p * W2p * 4) return;
+    const int q = idx & 3, pix = idx >> 2;
+    const int i = pix / W2p, j = pix - i * W2p;
+    const int u = 2 * (i - 1) + (q >> 1), v = 2 * (j - 1) + (q & 1);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i > 0 && j > 0 && u < H && v < W) {
+        const size_t HW = (size_t)H * W, at = (size_t)u * W + v;
+        o = make_float4(__ldg(x + at), __ldg(x + HW + at), __ldg(x + 2 * HW + at), 0.f);
+    }
+    *reinterpret_cast<float4*>(y + (size_t)idx * 4) = o;
+}
+
 // generic [N,C,HW] -> [N,HW,C] (smem-tiled transpose)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int ldy) {
     __shared__ float t[32][33];
@@ -290,6 +309,13 @@ extern "C" int aoc_image_to_nhwc4_f32(const float* x, float* y, int H, int W, cu
     AOC_CHECK_ARG(x && y && H > 0 && W > 0, "bad args");
     nchw3_to_nhwc4_kernel<<<cdiv((long long)H * W, 256), 256, 0, stream>>>(x, y, H * W);
     return launch_status("aoc_image_to_nhwc4_f32");
+}
+
+extern "C" int aoc_image_to_s2d16_f32(const float* x, float* y, int H, int W, cudaStream_t stream) {
+    AOC_CHECK_ARG(x && y && H > 0 && W > 0, "bad args");
+    const int H2p = (H + 1) / 2 + 1, W2p = (W + 1) / 2 + 1;
+    image_to_s2d16_kernel<<<cdiv((long long)H2p * W2p * 4, 256), 256, 0, stream>>>(x, y, H, W, H2p, W2p);
+    return launch_status("aoc_image_to_s2d16_f32");
 }
 
 extern "C" int aoc_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int HW, int ldy, cudaStream_t stream) {

@@ -85,6 +85,19 @@ class Weights:
 
         bb = "feature_extracter.backbone"
         add_conv(bb + ".conv1", bb + ".bn1", pad_cin=4)
+        # the stem as a 4x4 / stride-1 convolution over the space-to-depth frame (aoc_image_to_s2d16_f32): tap a' of the 4
+        # and source-row parity py cover source tap r = 2 a' + py - 1 of the 7 (r = -1: no such tap, zero weights)
+        w7 = self.conv[bb + ".conv1"][0]                                  # [64][7][7][4], BatchNorm folded
+        w4 = w7.new_zeros(w7.shape[0], 4, 4, 16)
+        for a_ in range(4):
+            for py in (0, 1):
+                r = 2 * a_ + py - 1
+                for b_ in range(4):
+                    for px in (0, 1):
+                        s_ = 2 * b_ + px - 1
+                        if 0 <= r <= 6 and 0 <= s_ <= 6:
+                            w4[:, a_, b_, (py * 2 + px) * 4:(py * 2 + px) * 4 + 4] = w7[:, r, s_, :]
+        self.conv[bb + ".conv1.s2d"] = (w4.contiguous(), self.conv[bb + ".conv1"][1], tuple(w4.shape))
         for lname, blocks in (("layer1", 3), ("layer2", 4), ("layer3", 23), ("layer4", 3)):
             for i in range(blocks):
                 p = "%s.%s.%d" % (bb, lname, i)
@@ -203,6 +216,7 @@ class Engine:
         # (default: plain launches -- 15 kernels, ~40 us of host time per frame, nothing to re-capture at a bank change; the
         # re-capture cost 0.3 ms per change and, sporadically, a 50-120 ms stall of the instantiation)
         self.segf_graph = os.environ.get("AOCB200_SEGF_GRAPH", "0") != "0"
+        self.stem_s2d = os.environ.get("AOCB200_STEM_S2D", "1") != "0"      # space-to-depth stem (0: the 7x7 / stride-2 form)
         self._segA, self._static = {}, {}
         self._cap_stream = self._pool = None
         self._gt_cache = (None, 0, 0)
@@ -415,10 +429,17 @@ class Engine:
         assert img.dim() == 4 and img.shape[0] == 1 and img.shape[1] == 3
         img = img.to(device=self.dev, dtype=torch.float32).contiguous()
         H, W = int(img.shape[2]), int(img.shape[3])
-        x4 = self.new(1, H, W, 4)
-        L.image_to_nhwc4_f32(img.data_ptr(), x4.ptr, H, W, self.stream)
         bb = "feature_extracter.backbone"
-        x = self.conv(x4, bb + ".conv1", stride=2, pad=3, relu=True)
+        if self.stem_s2d:
+            # resnet.py:108-110 (7x7 / stride 2 / pad 3) as a 4x4 / stride-1 / pad-1 convolution over the space-to-depth
+            # frame: 16 stages of 16 real channels instead of 49 stages of 4 real channels padded to 16
+            x16 = self.new(1, (H + 1) // 2 + 1, (W + 1) // 2 + 1, 16)
+            L.image_to_s2d16_f32(img.data_ptr(), x16.ptr, H, W, self.stream)
+            x = self.conv(x16, bb + ".conv1.s2d", stride=1, pad=1, relu=True)
+        else:
+            x4 = self.new(1, H, W, 4)
+            L.image_to_nhwc4_f32(img.data_ptr(), x4.ptr, H, W, self.stream)
+            x = self.conv(x4, bb + ".conv1", stride=2, pad=3, relu=True)
         Hp, Wp = (x.H + 2 - 3) // 2 + 1, (x.W + 2 - 3) // 2 + 1
         xp = self.new(1, Hp, Wp, 64)
         L.maxpool3x3s2_nhwc_f32(x.ptr, xp.ptr, 1, x.H, x.W, 64, self.stream)

@@ -154,6 +154,11 @@ int aoc_delta_sum_f32(const float* v, float* out, int N, int C, int ldo, cudaStr
 
 /* ---------------------------------------------------------------- layout / resampling (resize.cu) */
 int aoc_image_to_nhwc4_f32(const float* x_chw3, float* y_hwc4, int H, int W, cudaStream_t stream);
+/* Space-to-depth form of the frame for the ResNet stem (resnet.py:108-110: 7x7 / stride 2 / pad 3): y is
+ * [ceil(H/2) + 1][ceil(W/2) + 1][16], pixel (i, j) = the 2x2 source block at (2(i-1), 2(j-1)) as channels (py*2+px)*4 + c,
+ * zero outside the image, in row 0 / column 0 and in every c = 3.  The stem is then a 4x4 / stride-1 / pad-1 convolution
+ * over y (weights rearranged by the caller: source tap r = 2a' + py - 1), 16 K stages instead of 49. */
+int aoc_image_to_s2d16_f32(const float* x_chw3, float* y_s2d, int H, int W, cudaStream_t stream);
 int aoc_nchw_to_nhwc_f32(const float* x, float* y, int N, int C, int HW, int ldy, cudaStream_t stream);
 int aoc_nhwc_to_nchw_f32(const float* x, float* y, int N, int C, int HW, int ldx, cudaStream_t stream);
 /* F.interpolate(mode='bilinear', align_corners=True); with (ids, table) the source is table[ids[pixel]] */

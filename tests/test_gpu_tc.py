@@ -89,6 +89,31 @@ def _conv_tc_case(eng, N, H, W, Cin, Cout, k, stride, pad, dil, relu=False, res=
     return e_tc, e_32
 
 
+def test_stem_space_to_depth(eng, state_dict):
+    """resnet.py:108-110 -- the 7x7 / stride-2 / pad-3 stem -- evaluated as a 4x4 / stride-1 convolution over the
+    space-to-depth frame (aoc_image_to_s2d16_f32 + rearranged weights) against the float64 evaluation of the ORIGINAL
+    convolution with the folded weights, odd and even image sizes; the 7x7 form of the same kernel is the yardstick."""
+    eng.tc_conv = True
+    name = "feature_extracter.backbone.conv1"
+    w7, b7, _ = eng.w.conv[name]
+    w = w7[..., :3].permute(0, 3, 1, 2).double().cpu()
+    for H, W, seed in ((65, 97, 1), (64, 98, 2), (129, 80, 3)):
+        img = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(seed))
+        want = F.relu(F.conv2d(img.double(), w, b7.double().cpu(), 2, 3))
+        x4 = eng.new(1, H, W, 4)
+        eng.L.image_to_nhwc4_f32(img.cuda().data_ptr(), x4.ptr, H, W, eng.stream)
+        y7 = eng.conv(x4, name, stride=2, pad=3, relu=True)
+        x16 = eng.new(1, (H + 1) // 2 + 1, (W + 1) // 2 + 1, 16)
+        eng.L.image_to_s2d16_f32(img.cuda().data_ptr(), x16.ptr, H, W, eng.stream)
+        y4 = eng.conv(x16, name + ".s2d", stride=1, pad=1, relu=True)
+        torch.cuda.synchronize()
+        assert (y4.H, y4.W) == (y7.H, y7.W) == tuple(want.shape[2:])
+        e4 = (from_T(y4).double() - want).abs().max().item()
+        e7 = (from_T(y7).double() - want).abs().max().item()
+        print("[parity] stem %dx%d: |s2d-fp64|=%.3e  |7x7-fp64|=%.3e (range %.2f)" % (H, W, e4, e7, want.abs().max().item()))
+        assert e4 <= 2.0 * e7 + 2.4e-7 * want.abs().max().item(), (e4, e7)
+
+
 def test_conv_tc_vs_fp64(eng):
     eng.tc_conv = True
     c = _conv_tc_case
