@@ -173,6 +173,8 @@ class _Graph:
     def replay(self):
         self.g.replay()
         self.L.launches += self.n
+        if self.L.profile is not None:
+            self.L.replayed.add(id(self))       # bench.py's in-graph kernel timing reads the events of replayed graphs
 
 
 class Engine:
@@ -945,8 +947,7 @@ class Engine:
         self.overflow_frames.append(frame)
         self.conv_mode = 0
         self.L.fill_u32(self._ovf.data_ptr(), 0, 1, self.stream)
-        self._segA.clear(); self._static.clear()            # graphs captured with split-fp16 kernels / weight images
-        self._cap_stream = self._pool = None                # (their memory pool dies with its last graph: take a new one)
+        self.drop_graphs()                                  # graphs captured with split-fp16 kernels / weight images
         for slot in self._ovf_ring:
             slot[2][0] = None
         msg = ("aocb200: a convolution input of frame %d reached the fp16 range (|x| >= 6e4); the split-fp16 operand "
@@ -1025,6 +1026,11 @@ class Engine:
     #   C  local matching + decoder + softmax                                           (per size / object count)
     # Inputs owned by the caller (previous embedding / mask, decoder memory) are copied into static buffers before the
     # replay; everything handed back is a fresh copy, so the caller's bank never aliases a recycled buffer.
+    def drop_graphs(self):
+        """forget every captured segment and its static buffers (the next frame captures afresh)"""
+        self._segA.clear(); self._static.clear()
+        self._cap_stream = self._pool = None                # (their memory pool dies with its last graph: take a new one)
+
     def _capture(self, fn):
         L = self.L
         n0 = L.launches
@@ -1036,16 +1042,19 @@ class Engine:
             self._pool = torch.cuda.graph_pool_handle()
         cur = torch.cuda.current_stream(self.dev)
         self._cap_stream.wait_stream(cur)
+        gr = _Graph(g, 0, L)
         with torch.cuda.stream(self._cap_stream):
             g.capture_begin(pool=self._pool)
+            L.capture_tag = id(gr)
             try:
                 out = fn()
             finally:
+                L.capture_tag = None
                 g.capture_end()
         cur.wait_stream(self._cap_stream)
-        n = L.launches - n0
+        gr.n = L.launches - n0
         L.launches = n0                     # captured, not executed: every replay() accounts for its kernels
-        return _Graph(g, n, L), out
+        return gr, out
 
     def _forward_graphed(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,
                          pred_size, gt_ids):

@@ -66,6 +66,12 @@ class _Lib:
         self.launches = 0          # kernels launched through this binding (see KERNELS_PER_CALL)
         self.calls = 0
         self.profile = None        # {entry point name: [(start_event, end_event, args), ...]} when profiling
+        # calls made while a CUDA graph is being captured are bracketed by EXTERNAL events (event-record nodes of the
+        # graph, re-recorded by every replay): {entry point name: [(start, end, args, capture tag), ...]}; the engine
+        # sets `capture_tag` around a capture and adds the tag of every replayed graph to `replayed`
+        self.profile_graph = {}
+        self.capture_tag = None
+        self.replayed = set()
         for name, (ret, args) in self.protos.items():
             fn = getattr(self.cdll, name)
             fn.restype = _ctype(ret) if ret != "int" else ctypes.c_int
@@ -83,11 +89,15 @@ class _Lib:
             prof = self.profile
             if prof is not None and name in prof:
                 import torch
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                cap = torch.cuda.is_current_stream_capturing()
+                e0, e1 = (torch.cuda.Event(enable_timing=True, external=cap) for _ in range(2))
                 e0.record()
                 rc = fn(*a)
                 e1.record()
-                prof[name].append((e0, e1, a))
+                if cap:
+                    self.profile_graph.setdefault(name, []).append((e0, e1, a, self.capture_tag))
+                else:
+                    prof[name].append((e0, e1, a))
             else:
                 rc = fn(*a)
             if rc != 0:

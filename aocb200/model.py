@@ -50,6 +50,14 @@ class AOCNetB200(ParamTree):
             self._engine = Engine(self.state_dict(), dev)
         return self._engine
 
+    def reserve_memory(self, nbytes):
+        """Serving knob (no counterpart in the reference): make torch's caching allocator hold `nbytes` of device memory
+        as ONE free cached segment, from which the per-frame result tensors and the growing bank (one 10 MB embedding
+        per stored frame at 480p) are then split without a cudaMalloc -- a cudaMalloc next to running graphs was measured
+        at 20-100 ms, i.e. several frames, whenever the allocator had to grow in the middle of a sequence."""
+        dev = next(iter(self.parameters())).device
+        torch.empty(int(nbytes), dtype=torch.uint8, device=dev)      # freed at once: stays cached, splittable
+
     # -- reference API ---------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_for_eval(self, memory_prev_list, ref_embeddings, ref_masks, prev_embedding, prev_mask, current_frame,

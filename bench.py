@@ -255,57 +255,68 @@ def timed_run(model, frames, first, device, steps, warmup, host_io, dist, sample
 
 
 def kernel_profile(model, frames, first, device, n_frames):
-    """CUDA-event duration of every launch of the two tensor-core kernels over `n_frames` predicted frames."""
+    """CUDA-event duration of every launch of the named kernels over `n_frames` predicted frames, measured INSIDE the
+    replayed CUDA graphs of the product path: the segments are captured afresh with an external event pair (event-record
+    graph nodes) around each profiled entry point, so every replay re-records them on the device -- no host launch gap
+    inside a pair (per-launch events around plain launches charged ~10 us of host time to each of the ~100 short
+    convolutions of a frame).  The bank-dependent segment runs as plain launches in the product path and is timed so."""
     from aocb200.lib import lib
     L = lib()
     np.random.seed(77)
     eng = model.engine()
-    graphs, eng.use_graphs = eng.use_graphs, False      # per-launch events need plain launches: same kernels, same
-    st = Stepper(model, frames, first, K_OBJ, device, False)   # shapes, just not replayed from the captured graphs
-    for _ in range(2):
+    torch.cuda.synchronize()
+    eng.drop_graphs()
+    names = ("aoc_conv2d_nhwc_tc", "aoc_global_match_tc", "aoc_global_match_tc_sharded", "aoc_kmeans_proxies_f32",
+             "aoc_affine_stats_nc_f32", "aoc_channel_stats_f32", "aoc_cond_phi_f32")
+    L.profile = {n: [] for n in names}
+    L.profile_graph = {}
+    prof = {n: [] for n in names}        # (milliseconds, args) per launch, frame-major
+    st = Stepper(model, frames, first, K_OBJ, device, False)
+    for _ in range(2):                   # captures every segment variant (with / without decoder memory)
         st.step()
-    L.profile = {"aoc_conv2d_nhwc_tc": [], "aoc_global_match_tc": [], "aoc_global_match_tc_sharded": [],
-                 "aoc_kmeans_proxies_f32": [],
-                 "aoc_affine_stats_nc_f32": [], "aoc_channel_stats_f32": [], "aoc_cond_phi_f32": []}
     km_rows = []
+    per_frame = {n: [] for n in names}
     for _ in range(n_frames):
+        for n in names:
+            L.profile[n] = []
+        L.replayed = set()
         st.step()
         km_rows.append(sum(eng.bank.index["counts"]) if eng.bank.index else 0)    # bank pixels carrying an object id
-    torch.cuda.synchronize()
-    prof, L.profile = L.profile, None
-    eng.use_graphs = graphs
+        torch.cuda.synchronize()
+        for n in names:
+            got = [(e0.elapsed_time(e1), a) for e0, e1, a in L.profile[n]]
+            got += [(e0.elapsed_time(e1), a) for e0, e1, a, tag in L.profile_graph.get(n, ()) if tag in L.replayed]
+            prof[n] += got
+            per_frame[n].append(sum(ms for ms, _ in got))
+    L.profile = None
+    L.profile_graph = {}
+    eng.drop_graphs()                    # the event nodes go with the graphs
     out = {}
     conv = prof["aoc_conv2d_nhwc_tc"]
     if conv:
         fl, ms = 0.0, 0.0
         names = [n for _, n in L.protos["aoc_conv2d_nhwc_tc"][1]]       # argument positions from the header itself
         ix = [names.index(n) for n in ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil")]
-        per = len(conv) // n_frames                 # the same 161 layers every frame
-        frame_ms = [0.0] * n_frames
-        for i, (e0, e1, a) in enumerate(conv):
+        for t_ms, a in conv:
             N, H, W, Cin, Cout, kh, kw, stride, pad, dil = (a[i_] for i_ in ix)
             Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
             Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
             fl += 2.0 * N * Ho * Wo * Cout * kh * kw * Cin
-            frame_ms[min(i // per, n_frames - 1)] += e0.elapsed_time(e1)
-        # plain launches: an event pair also sees the host when the stream runs dry, and ONE host pause (3 ms, seen once
-        # in seven runs) inside one pair moved the per-frame average by 0.5 ms -- the per-frame sums are identical work,
-        # so the MEDIAN frame x n_frames is the robust total (equal to the sum when nothing stalls)
-        ms = sorted(frame_ms)[n_frames // 2] * n_frames if len(conv) == per * n_frames else sum(frame_ms)
+        ms = sum(per_frame["aoc_conv2d_nhwc_tc"])
         out["conv"] = {"launches": len(conv), "ms": ms, "flop": fl}
     gm = prof["aoc_global_match_tc"] + prof["aoc_global_match_tc_sharded"]
     if gm:
         fl, ms = 0.0, 0.0
-        for e0, e1, a in gm:
+        for t_ms, a in gm:
             share = 1.0 / a[9] if len(a) > 12 else 1.0      # sharded: this rank contracts 1 / world of the bank rows
             fl += 2.0 * a[1] * a[5] * 100 * share           # HW x (padded) bank rows x C
-            ms += e0.elapsed_time(e1)
+            ms += t_ms
         out["match"] = {"launches": len(gm), "ms": ms, "flop": fl}
     km = prof["aoc_kmeans_proxies_f32"]
     if km:
-        ms = sum(e0.elapsed_time(e1) for e0, e1, a in km)
+        ms = sum(t_ms for t_ms, a in km)
         names = [n for _, n in L.protos["aoc_kmeans_proxies_f32"][1]]
-        iters = km[0][2][names.index("iters")]
+        iters = km[0][1][names.index("iters")]
         # SURVEY 8d: algorithmic bytes of the adaptive-proxy step = iters * (bank rows with an object) * 100 floats
         out["kmeans"] = {"launches": len(km), "ms": ms, "bytes": float(iters) * sum(km_rows) * 400.0,
                          "kernels_per_call": 1}
@@ -316,16 +327,16 @@ def kernel_profile(model, frames, first, device, n_frames):
     if af:       # GroupNorm apply (+ residual, ReLU) with the next block's GCT statistics: 1 read (+1 residual) + 1 write
         fn = "aoc_affine_stats_nc_f32"
         by = sum(4.0 * arg("N", fn, a) * arg("HW", fn, a) * arg("C", fn, a) * (3 if arg("residual", fn, a) else 2)
-                 for _, _, a in af)
-        out["affine_stats"] = {"launches": len(af), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in af), "bytes": by,
+                 for _, a in af)
+        out["affine_stats"] = {"launches": len(af), "ms": sum(t_ms for t_ms, _ in af), "bytes": by,
                                "kernels_per_call": 2}
     cs = prof["aoc_channel_stats_f32"] + prof["aoc_cond_phi_f32"]
     if cs:       # FiLM conditioning layer (phi map pass + masked pooling pass) and the remaining statistics passes: 1 read each
         by = sum(4.0 * arg("N", "aoc_channel_stats_f32", a) * arg("HW", "aoc_channel_stats_f32", a) *
-                 arg("C", "aoc_channel_stats_f32", a) for _, _, a in prof["aoc_channel_stats_f32"])
+                 arg("C", "aoc_channel_stats_f32", a) for _, a in prof["aoc_channel_stats_f32"])
         by += sum(4.0 * arg("N", "aoc_cond_phi_f32", a) * arg("HW", "aoc_cond_phi_f32", a) * arg("C", "aoc_cond_phi_f32", a)
-                  for _, _, a in prof["aoc_cond_phi_f32"])
-        out["film_stats"] = {"launches": len(cs), "ms": sum(e0.elapsed_time(e1) for e0, e1, _ in cs), "bytes": by,
+                  for _, a in prof["aoc_cond_phi_f32"])
+        out["film_stats"] = {"launches": len(cs), "ms": sum(t_ms for t_ms, _ in cs), "bytes": by,
                              "kernels_per_call": 2}
     out["frames"] = n_frames
     return out
@@ -488,6 +499,10 @@ def main():
             pre.step()
         torch.cuda.synchronize()
         del pre
+    # the pre-roll leaves the allocator with the segments of ITS request order; a timed run whose requests interleave
+    # differently could still grow the pool (seen once in ~10 runs: one cudaMalloc, 58 ms, inside the end-to-end run):
+    # hold a free cached segment a sequence can split its tensors from (AOCNetB200.reserve_memory)
+    model.reserve_memory(2 << 30)
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches, clocks = timed_run(model, frames, first, device, args.steps, args.warmup, False, dist, sampler)
@@ -543,7 +558,7 @@ def main():
                               "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"] + " HBM copy",
                               "launches_per_step": p["launches"] * p["kernels_per_call"] / prof["frames"],
                               "ms_per_step": p["ms"] / prof["frames"], "share_of_step": p["ms"] / prof["frames"] / step_ms,
-                              "note": note + "; timed per C-ABI call with CUDA events (plain launches)"}
+                              "note": note + "; timed per C-ABI call with CUDA events (event-record nodes inside the replayed graphs; plain launches for the bank-dependent segment, as in the product path)"}
         dom = max(roofs.values(), key=lambda r: r["ms_per_step"]) if roofs else None
         line["roofline"] = dom
         line["roofline_all"] = roofs

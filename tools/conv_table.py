@@ -1,5 +1,6 @@
 """Per-layer table of the convolution calls of one steady-state frame (480p, 5 objects): shape, flags, CUDA-event time.
-Plain launches (no graph replay) so that events can bracket each call; small layers include some launch gap."""
+Timed INSIDE the replayed CUDA graphs of the product path (external event pairs = event-record nodes around each call,
+see aocb200/lib.py), so a row carries no host launch gap."""
 import os
 import sys
 from collections import OrderedDict
@@ -23,30 +24,35 @@ def main():
     model = get_module()(None, None)
     model.load_state_dict(synthetic_state_dict(1234))
     model = model.cuda(0).eval()
-    model.engine().use_graphs = False
     np.random.seed(0)
+    L = lib()
+    L.profile = {"aoc_conv2d_nhwc_tc": []}
     st = Stepper(model, frames, labels[0], K, dev, False)
     for _ in range(3):
         st.step()
-    L = lib()
     names = [n for _, n in L.protos["aoc_conv2d_nhwc_tc"][1]]
     ix = {n: names.index(n) for n in names}
     reps = 3
-    L.profile = {"aoc_conv2d_nhwc_tc": []}
+    prof = []
     for _ in range(reps):
+        L.profile["aoc_conv2d_nhwc_tc"] = []
+        L.replayed = set()
         st.step()
-    torch.cuda.synchronize()
-    prof, L.profile = L.profile["aoc_conv2d_nhwc_tc"], None
+        torch.cuda.synchronize()
+        prof += [(e0.elapsed_time(e1), a) for e0, e1, a in L.profile["aoc_conv2d_nhwc_tc"]]
+        prof += [(e0.elapsed_time(e1), a) for e0, e1, a, tag in L.profile_graph.get("aoc_conv2d_nhwc_tc", ())
+                 if tag in L.replayed]
+    L.profile = None
     per = len(prof) // reps
     tab = OrderedDict()
-    for i, (e0, e1, a) in enumerate(prof):
+    for i, (t_ms, a) in enumerate(prof):
         g = lambda n: a[ix[n]]
         key = (g("N"), g("H"), g("W"), g("Cin"), g("Cout"), g("kh"), g("stride"), g("dil"),
                "aff" if (g("in_a") or g("in_b") or g("in_relu")) else "-", "res" if g("residual") else "-",
                "stats" if g("tile_stats") else "-")
         t = tab.setdefault(key, [0, 0.0])
         t[0] += 1
-        t[1] += e0.elapsed_time(e1) * 1e3
+        t[1] += t_ms * 1e3
     tot = sum(v[1] for v in tab.values()) / reps
     print("%d conv calls per frame, %.1f us per frame" % (per, tot))
     print("%3s %4s %4s %5s %5s k s d  %-5s %-4s %-6s %5s %9s %9s %8s" % ("N", "H", "W", "Cin", "Cout", "aff", "res", "stats", "calls",
