@@ -13,7 +13,7 @@ namespace aoc {
 
 // part layout: [N][S][2][C] doubles (sum, sum of squares).  MASKED: weight = phi[n,p] > thr[n] (strict).
 template <bool MASKED>
-__global__ void __launch_bounds__(256) channel_stats_partial(const float* __restrict__ x, int HW, int C, int ldx,
+__global__ void __launch_bounds__(256, 6) channel_stats_partial(const float* __restrict__ x, int HW, int C, int ldx,
                                                               int PB, int CW, const float* __restrict__ phi,
                                                               const float* __restrict__ thr,
                                                               double* __restrict__ part) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) channel_stats_partial(const float* __rest
 // y = x*a + b (+ res*ra) (ReLU) AND the per-(sample, channel) sum / sum of squares of y in the same pass (the GCT gate /
 // global average pool of the next block then needs no pass of its own).  Same slab decomposition and fixed reduction
 // order as channel_stats_partial; part layout [N][S][2][C] doubles.
-__global__ void __launch_bounds__(256) affine_stats_partial(const float* __restrict__ x, const float* __restrict__ a,
+__global__ void __launch_bounds__(256, 4) affine_stats_partial(const float* __restrict__ x, const float* __restrict__ a,
                                                              const float* __restrict__ b, const float* __restrict__ res,
                                                              const float* __restrict__ res_scale, float* __restrict__ y,
                                                              int HW, int C, int ldx, int ldy, int ldres, int relu, int PB,
@@ -345,14 +345,22 @@ __global__ void __launch_bounds__(256) gn_coeffs_tiles_kernel(const float* __res
     }
 }
 
-// pixels per slab (= per block) of the statistics kernels: 256, halved down to 32 while the launch has fewer than four
-// blocks per SM (N = 1 maps of the backbone: the global average pool over 31 x 54 x 2048 ran on 14 blocks, 77 us for 14 MB)
-static int stats_slab(int N, int HW, int C) {
-    int pb = 256;
-    while ((long long)cdiv(HW, pb) > 1024) pb *= 2;
-    const long long z = cdiv(C, 1024);
-    while (pb > 32 && (long long)cdiv(HW, pb) * N * z < 4 * 148) pb /= 2;
-    return pb;
+// pixels per slab (= per block) of the statistics kernels.  The blocks of a launch are equal pieces of work, so a grid a few
+// blocks LARGER than what the chip holds at once runs for two block lifetimes instead of one: 6 x 101 = 606 slabs of 256
+// pixels (121 x 213 map, six objects) on 148 x 4 = 592 resident blocks was the common case, and 6 x 102 = 612 slabs of 64
+// pixels at half resolution likewise.  The slab is therefore sized so that the grid is a whole number of waves: `bps`
+// resident blocks per SM (held by __launch_bounds__), waves = what the nominal 256-pixel slab would need, rounded DOWN
+// (slabs of 256 .. 511 pixels); small launches (N = 1 maps of the backbone) get one wave of slabs of at least 32 pixels.
+constexpr int STATS_BPS = 6, AFFINE_STATS_BPS = 4;      // = minBlocksPerMultiprocessor of the two partial kernels
+static int stats_slab(int N, int HW, int C, int bps) {
+    const long long z = cdiv(C, 1024), R = 148LL * bps;
+    const long long nominal = (long long)cdiv(HW, 256) * N * z;
+    const long long waves = nominal / R > 0 ? nominal / R : 1;
+    long long S = waves * R / ((long long)N * z);
+    if (S < 1) S = 1;
+    if (S > 1024) S = 1024;
+    int pb = cdiv(HW, (int)S);
+    return pb < 32 ? 32 : pb;
 }
 
 }  // namespace aoc
@@ -360,9 +368,8 @@ static int stats_slab(int N, int HW, int C) {
 using namespace aoc;
 
 extern "C" size_t aoc_channel_stats_workspace_bytes(int N, int HW, int C) {
-    int PB = stats_slab(N, HW, C);
-    size_t S = (size_t)cdiv(HW, PB);
-    return (size_t)N * S * 2 * C * sizeof(double);
+    const int Sa = cdiv(HW, stats_slab(N, HW, C, STATS_BPS)), Sb = cdiv(HW, stats_slab(N, HW, C, AFFINE_STATS_BPS));
+    return (size_t)N * (size_t)(Sa > Sb ? Sa : Sb) * 2 * C * sizeof(double);       // serves both entry points
 }
 
 // stats out: [N][2][C] doubles (sum, sumsq).  phi/thr optional (masked sum: only pixels with phi > thr[n]).
@@ -374,7 +381,7 @@ extern "C" int aoc_channel_stats_f32(const float* x, int N, int HW, int C, int l
     AOC_CHECK_ARG((((uintptr_t)x) & 15) == 0, "x must be 16-byte aligned");
     AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
     AOC_CHECK_ARG((phi == nullptr) == (thr == nullptr), "phi and thr go together");
-    int PB = stats_slab(N, HW, C);
+    int PB = stats_slab(N, HW, C, STATS_BPS);
     int S = cdiv(HW, PB);
     int CW = C < 1024 ? C : 1024;
     int PL = 256 / (CW / 4);
@@ -401,7 +408,7 @@ extern "C" int aoc_affine_stats_nc_f32(const float* x, const float* a, const flo
                   "C (<= 1024) and the row strides must be multiples of 4");
     AOC_CHECK_ARG(((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)a)) & 15) == 0, "pointers must be 16-byte aligned");
     AOC_CHECK_ARG(ws_bytes >= aoc_channel_stats_workspace_bytes(N, HW, C), "workspace too small");
-    int PB = stats_slab(N, HW, C);
+    int PB = stats_slab(N, HW, C, AFFINE_STATS_BPS);
     int S = cdiv(HW, PB);
     int PL = 256 / (C / 4);
     size_t smem = (size_t)PL * 2 * C * sizeof(float);

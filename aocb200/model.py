@@ -50,13 +50,17 @@ class AOCNetB200(ParamTree):
             self._engine = Engine(self.state_dict(), dev)
         return self._engine
 
-    def reserve_memory(self, nbytes):
+    def reserve_memory(self, nbytes, small_mb=64):
         """Serving knob (no counterpart in the reference): make torch's caching allocator hold `nbytes` of device memory
         as ONE free cached segment, from which the per-frame result tensors and the growing bank (one 10 MB embedding
         per stored frame at 480p) are then split without a cudaMalloc -- a cudaMalloc next to running graphs was measured
         at 20-100 ms, i.e. several frames, whenever the allocator had to grow in the middle of a sequence."""
         dev = next(iter(self.parameters())).device
         torch.empty(int(nbytes), dtype=torch.uint8, device=dev)      # freed at once: stays cached, splittable
+        # tensors of <= 1 MB (the uint8 label maps a sequence keeps per stored frame) come from the allocator's SMALL pool,
+        # 2 MB segments of their own: the one cudaMalloc left inside a 26-frame run was such a segment (allocator trace)
+        small = [torch.empty(1 << 20, dtype=torch.uint8, device=dev) for _ in range(int(small_mb))]
+        del small
 
     # -- reference API ---------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -506,7 +506,19 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms, st, launches, clocks = timed_run(model, frames, first, device, args.steps, args.warmup, False, dist, sampler)
+    trace_alloc = os.environ.get("AOCB200_ALLOC_TRACE") == "1"       # diagnostic: who grows the allocator inside the e2e run
+    if trace_alloc:
+        torch.cuda.memory._record_memory_history(max_entries=200000)
     ms_e2e, st2, _, _ = timed_run(model, frames, first, device, args.steps, args.warmup, True, dist)
+    if trace_alloc:
+        snap = torch.cuda.memory._snapshot()
+        torch.cuda.memory._record_memory_history(enabled=None)
+        for tr in snap["device_traces"]:
+            for ev in tr:
+                if ev["action"] in ("segment_alloc", "segment_free", "oom"):
+                    print("[alloc-trace]", ev["action"], ev["size"], "stream", ev.get("stream"), " <- ".join(
+                        "%s:%d %s" % (os.path.basename(f["filename"]), f["line"], f["name"]) for f in ev.get("frames", [])[:14]),
+                        file=sys.stderr)
     seqs = 1 if SHARD else world
     value = seqs * args.steps / (ms / 1000.0)
     e2e = seqs * args.steps / (ms_e2e / 1000.0)

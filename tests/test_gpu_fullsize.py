@@ -104,6 +104,42 @@ def test_480p_k5_vs_oracle(model, state_dict):
             prev_o, prev_e, prev_c, prev_g = eo, ee, mask, masks_g[-1]
 
 
+def test_480p_k5_vs_reference_fixture(model):
+    """The engine against the REFERENCE ITSELF at BASELINE.json's headline configuration: tests/golden/full480_k5_ref.npz
+    holds the logits and label maps the repaired reference (tools/ref_loader.py) produced on this clip / these weights /
+    this numpy stream (tools/make_ref480_golden.py); frame 2 is teacher-forced with the reference's frame-1 label map (the
+    k-means draws depend on per-object pixel counts), so it sees a two-frame bank and a filled decoder memory.  The
+    oracle sits 3.6e-4 / 3.3e-4 from the same vectors (tests/test_oracle_golden.py)."""
+    import os
+    from aocb200.synth import make_clip
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "full480_k5_ref.npz"))
+    seed, K, H, W, n_pred = (int(g[k]) for k in ("seed", "K", "H", "W", "n_pred"))
+    frames, labels = make_clip(seed, H, W, K, n_pred + 1)
+    dev = torch.device("cuda:0")
+    eng = model.engine()
+    gt = torch.tensor([K], device=dev)
+    with torch.no_grad():
+        _, emb, mem = model.forward_for_eval([[None, None]], [], [], None, None, frames[0:1].to(dev), [H, W], gt)
+        lab = labels[0].view(1, 1, H, W).long().to(dev)
+        refs, masks, prev_e, prev_m = [emb], [lab], emb, lab
+        for t in range(1, n_pred + 1):
+            np.random.seed(seed if t == 1 else 100 * seed + t)
+            probs, emb, mem = model.forward_for_eval(mem, refs, masks, prev_e, prev_m, frames[t:t + 1].to(dev), [H, W], gt)
+            ref_l = torch.from_numpy(g["logits"][t - 1])
+            d = (eng.last_logits.reshape(K + 1, -1).cpu() - ref_l).abs().max().item()
+            ref_pred = torch.from_numpy(g["preds"][t - 1])
+            bad = int((torch.argmax(probs[0], 0).to(torch.uint8).cpu() != ref_pred).sum())
+            print("[parity] engine vs REFERENCE, 480p K=5 frame %d: max|dlogit| %.3e (logit range %.1f), argmax differs at "
+                  "%d of %d px" % (t, d, ref_l.abs().max().item(), bad, ref_pred.numel()))
+            assert d <= REF480_BOUNDS[t - 1][0] and bad <= REF480_BOUNDS[t - 1][1], (t, d, bad)
+            m = ref_pred.view(1, 1, H, W).long().to(dev)
+            refs.append(emb); masks.append(m)
+            prev_e, prev_m = emb, m
+
+
+# (max |dlogit|, argmax pixels) per frame: observed x 1.5 / x 2 (B200, round 2; the [parity] lines the test prints)
+REF480_BOUNDS = [(2e-2, 400), (2e-2, 400)]
+
 # observed x 1.5 (B200, round 2): see the [parity] lines these tests print
 CFG_BOUNDS = {
     # name: (|engine - fp64| with pinned proxies, |engine - oracle fp32| with pinned proxies, argmax pixels differing)

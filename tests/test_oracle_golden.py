@@ -50,6 +50,35 @@ def test_oracle_matches_reference_fixture(path, state_dict):
         assert torch.equal(preds[t].to(torch.uint8), g["preds"][t]), t
 
 
+def test_oracle_matches_reference_at_480p(state_dict):
+    """BASELINE.json's headline configuration (cfg3: 481x849, 5 objects) against the REFERENCE's own outputs
+    (tests/golden/full480_k5_ref.npz, written by tools/make_ref480_golden.py from /root/reference): two predicted frames,
+    the second teacher-forced with the reference's frame-1 label map (two-frame bank, filled decoder memory).  Observed
+    when the fixture was made: 3.6e-4 / 3.3e-4 on logits of range 45 (both sides CPU fp32, different op composition), argmax
+    differing at 3 / 6 of 408 369 pixels; asserted at x 1.5 / x 2."""
+    torch.set_num_threads(os.cpu_count())
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "full480_k5_ref.npz"))
+    seed, K, H, W, n_pred = (int(g[k]) for k in ("seed", "K", "H", "W", "n_pred"))
+    frames, labels = make_clip(seed, H, W, K, n_pred + 1)
+    orc = AOCOracle(state_dict)
+    gt = torch.tensor([K])
+    with torch.no_grad():
+        _, emb, mem = orc.forward_for_eval([[None, None]], [], [], None, None, frames[0:1], [H, W], gt)
+        lab = labels[0].view(1, 1, H, W).long()
+        refs, masks, prev_e, prev_m = [emb], [lab], emb, lab
+        for t in range(1, n_pred + 1):
+            np.random.seed(seed if t == 1 else 100 * seed + t)
+            probs, emb, mem = orc.forward_for_eval(mem, refs, masks, prev_e, prev_m, frames[t:t + 1], [H, W], gt)
+            d = (orc.last_logits.reshape(K + 1, -1) - torch.from_numpy(g["logits"][t - 1])).abs().max().item()
+            ref_pred = torch.from_numpy(g["preds"][t - 1])
+            bad = int((torch.argmax(probs[0], 0).to(torch.uint8) != ref_pred).sum())
+            print("[parity] oracle vs reference, 480p K=5 frame %d: max|dlogit| %.3e, argmax differs at %d px" % (t, d, bad))
+            assert d <= 6e-4 and bad <= 12, (t, d, bad)
+            m = ref_pred.view(1, 1, H, W).long()
+            refs.append(emb); masks.append(m)
+            prev_e, prev_m = emb, m
+
+
 def test_kmeans_restatement_matches_scipy():
     from scipy.cluster.vq import kmeans2
     import warnings
