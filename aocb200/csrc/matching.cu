@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(128) proxy_match_kernel(const float* __restric
     __syncthreads();
     float q2 = 0.f;
     for (int c = 0; c < EMB; ++c) { float v = Qs[c * 128 + tid]; q2 = fmaf(v, v, q2); }
-    for (int o = blockIdx.y; o < O; o += gridDim.y) {      // one object per block (grid.y = O): see the launcher
+    for (int o = 0; o < O; ++o) {
         __syncthreads();
         for (int i = tid; i < NPX * EMB; i += 128) {
             int j = i / EMB, c = i - j * EMB;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(128) proxy_match_wide_kernel(const float* __re
     __syncthreads();
     float q2 = 0.f;
     for (int c = 0; c < EMB; ++c) { float v = Qs[c * 128 + tid]; q2 = fmaf(v, v, q2); }
-    for (int o = blockIdx.y; o < O; o += gridDim.y) {      // one object per block (grid.y = O): see the launcher
+    for (int o = 0; o < O; ++o) {
         float m0 = INFINITY, m1 = INFINITY, dp = 0.f;
         for (int s0 = 0; s0 <= 2 * kmax; s0 += 32) {          // last chunk: the mean proxy alone
             const int n = min(32, 2 * kmax + 1 - s0);
@@ -732,8 +732,8 @@ extern "C" int aoc_proxy_match_f32(const float* q, int HW, const float* P, const
         size_t smem_w = (size_t)(EMB * 128 + EMB * 32) * sizeof(float);
         if (attr_w.first())
             cudaFuncSetAttribute(proxy_match_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-        proxy_match_wide_kernel<<<dim3(cdiv(HW, 128), O), 128, smem_w, stream>>>(q, HW, P, pvalid, bias, O, kmax,
-                                                                               out_cluster, out_proxy);
+        proxy_match_wide_kernel<<<cdiv(HW, 128), 128, smem_w, stream>>>(q, HW, P, pvalid, bias, O, kmax, out_cluster,
+                                                                      out_proxy);
         return launch_status("aoc_proxy_match_f32");
     }
     static PerDeviceOnce attr_done;
@@ -741,10 +741,9 @@ extern "C" int aoc_proxy_match_f32(const float* q, int HW, const float* P, const
     if (attr_done.first()) {
         cudaFuncSetAttribute(proxy_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
-    // grid.y = objects: a 121 x 213 map is 202 query tiles -- 1.4 four-warp blocks per SM walking the objects one after the
-    // other ran at 9 % occupancy, latency bound (85 us for 0.1 GFLOP); the objects are independent, so each gets its own
-    // block (the 51 KB query tile is re-staged from L2 per object; per-proxy arithmetic unchanged, results bit-identical)
-    proxy_match_kernel<<<dim3(cdiv(HW, 128), O), 128, smem, stream>>>(q, HW, P, pvalid, bias, O, out_cluster, out_proxy);
+    // (one object per block -- grid.y = O, 1 212 blocks instead of 202 at 9 % occupancy -- was measured: 85 -> 98 us, the
+    // re-staged query tile and the third partial wave cost more than the occupancy gains)
+    proxy_match_kernel<<<cdiv(HW, 128), 128, smem, stream>>>(q, HW, P, pvalid, bias, O, out_cluster, out_proxy);
     return launch_status("aoc_proxy_match_f32");
 }
 

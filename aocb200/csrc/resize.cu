@@ -165,8 +165,8 @@ __global__ void resize_bicubic_kernel(const float* __restrict__ x, float* __rest
 // The decoder's only bicubic resize is an exact 2x upsampling with align_corners (61 x 107 -> 121 x 213: Ho = 2 Hi - 1), where
 // the four outputs (2i + a, 2j + b), a, b in {0, 1}, read the SAME 4 x 4 input patch (rows i-1..i+2, columns j-1..j+2).  One
 // thread computes the 2 x 2 block from one patch: 16 loads per four outputs instead of 16 per output (the general kernel
-// was bound by the L1 / LSU, 183 us for 158 MB of output); per output the arithmetic -- coefficients from the same
-// expression, the same fma order -- is that of resize_bicubic_kernel, so the results are bit-identical.
+// was bound by the L1 / LSU, 183 us for 158 MB of output); per output the arithmetic -- the same coefficients, the same fma
+// order, minus the terms whose weight is exactly zero -- is that of resize_bicubic_kernel, so the results are bit-identical.
 __global__ void __launch_bounds__(256) resize_bicubic2x_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi,
                                                                int Wi, int Ho, int Wo, int C, int ldx, int ldy, float sh, float sw) {
     const int C4 = C >> 2;
@@ -189,34 +189,49 @@ __global__ void __launch_bounds__(256) resize_bicubic2x_kernel(const float* __re
                 v[j][k] = ldg4(x + (b + (size_t)yy * Wi + xx) * ldx + c);
             }
         }
+        // With sh = sw = 1/2 exactly (the launcher's condition) the fractional position of an output is 0 (even index) or
+        // 1/2 (odd index), and cubic_coeffs() evaluates -- exactly, every intermediate is a small dyadic number -- to
+        // {0, 1, 0, 0} and {-3/32, 19/32, 19/32, -3/32}.  A zero weight leaves the fma chain of the general kernel unchanged
+        // (fma(0, v, r) = r for finite v) and a unit weight copies, so: (even, even) is the centre sample itself,
+        // (even, odd) / (odd, even) are ONE four-tap chain along the row / column through the centre, and only (odd, odd)
+        // needs the full 4 x 4 patch -- 112 instead of 320 fmas per thread, in the same order: bit-identical for finite inputs.
+        const float W0 = -0.09375f, W1 = 0.59375f;
+        const float wq[4] = {W0, W1, W1, W0};
+        const size_t orow = ((size_t)n * Ho + 2 * bi) * Wo + 2 * bj;
+        const bool has_x = 2 * bj + 1 < Wo, has_y = 2 * bi + 1 < Ho;
+        *reinterpret_cast<float4*>(y + orow * ldy + c) = v[1][1];
+        if (has_x) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int yo = 2 * bi + a;
-            if (yo >= Ho) continue;
-            const float ry = sh * (float)yo;                           // == bi + a / 2 exactly (sh = 0.5)
-            float wy[4];
-            cubic_coeffs(ry - floorf(ry), wy);
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-                const int xo = 2 * bj + bb;
-                if (xo >= Wo) continue;
-                const float rx = sw * (float)xo;
-                float wx[4];
-                cubic_coeffs(rx - floorf(rx), wx);
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        r.x = fmaf(wx[k], v[j][k].x, r.x); r.y = fmaf(wx[k], v[j][k].y, r.y);
-                        r.z = fmaf(wx[k], v[j][k].z, r.z); r.w = fmaf(wx[k], v[j][k].w, r.w);
-                    }
-                    o.x = fmaf(wy[j], r.x, o.x); o.y = fmaf(wy[j], r.y, o.y);
-                    o.z = fmaf(wy[j], r.z, o.z); o.w = fmaf(wy[j], r.w, o.w);
-                }
-                *reinterpret_cast<float4*>(y + (((size_t)n * Ho + yo) * Wo + xo) * ldy + c) = o;
+            for (int k = 0; k < 4; ++k) {
+                r.x = fmaf(wq[k], v[1][k].x, r.x); r.y = fmaf(wq[k], v[1][k].y, r.y);
+                r.z = fmaf(wq[k], v[1][k].z, r.z); r.w = fmaf(wq[k], v[1][k].w, r.w);
             }
+            *reinterpret_cast<float4*>(y + (orow + 1) * ldy + c) = r;
+        }
+        if (has_y) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o.x = fmaf(wq[j], v[j][1].x, o.x); o.y = fmaf(wq[j], v[j][1].y, o.y);
+                o.z = fmaf(wq[j], v[j][1].z, o.z); o.w = fmaf(wq[j], v[j][1].w, o.w);
+            }
+            *reinterpret_cast<float4*>(y + (orow + Wo) * ldy + c) = o;
+        }
+        if (has_x && has_y) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    r.x = fmaf(wq[k], v[j][k].x, r.x); r.y = fmaf(wq[k], v[j][k].y, r.y);
+                    r.z = fmaf(wq[k], v[j][k].z, r.z); r.w = fmaf(wq[k], v[j][k].w, r.w);
+                }
+                o.x = fmaf(wq[j], r.x, o.x); o.y = fmaf(wq[j], r.y, o.y);
+                o.z = fmaf(wq[j], r.z, o.z); o.w = fmaf(wq[j], r.w, o.w);
+            }
+            *reinterpret_cast<float4*>(y + (orow + Wo + 1) * ldy + c) = o;
         }
     }
 }

@@ -35,7 +35,8 @@ def test_version_and_error_string(built_lib):
 
 
 def test_workspace_queries(built_lib):
-    assert built_lib.channel_stats_workspace_bytes(6, 25773, 256) == 6 * 101 * 2 * 256 * 8
+    # whole-wave slabs (norm.cu::stats_slab): 6 samples x 148 slabs = one wave of 148 SMs x 6 resident blocks
+    assert built_lib.channel_stats_workspace_bytes(6, 25773, 256) == 6 * 148 * 2 * 256 * 8
     assert built_lib.bank_workspace_bytes(25773, 6) > 0
     assert built_lib.kmeans_workspace_bytes(25773, 6, 16) > 0
     assert built_lib.head_pool_workspace_bytes(25773) > 0
