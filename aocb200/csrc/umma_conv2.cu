@@ -301,7 +301,10 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp < C2_XW + 10) asm volatile("griddepcontrol.wait;" ::: "memory");       // transform, drain, TMA producers
+    // transform, drain and the activation TMA producer wait for the previous grid; the weight producer (warp C2_XW + 9) does
+    // NOT: the packed weight image is a constant of the model (complete before the first launch that uses it -- contract of
+    // aoc_conv2d_nhwc_tc), so its first ring of stages is fetched from HBM while the previous layer's last CTAs finish
+    if (warp < C2_XW + 9) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp < C2_XW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));

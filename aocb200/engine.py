@@ -310,6 +310,11 @@ class Engine:
                 buf = torch.empty(self.L.conv_packed_weight_bytes(Cout, Cin, kh, kw, mode), dtype=torch.uint8,
                                   device=self.dev)
                 self.L.conv_pack_weights(w.data_ptr(), Cout, Cin, kh, kw, mode, buf.data_ptr(), self.stream)
+                # the convolution's weight-copy warp does not wait for the preceding kernel of the stream (programmatic
+                # dependent launch: weights are constants, their first tiles are fetched under the previous layer's tail),
+                # so a packed image must be COMPLETE before its first use -- once per layer, on the warm-up pass
+                assert not torch.cuda.is_current_stream_capturing(), "weights are packed on the warm-up pass, not in a capture"
+                torch.cuda.synchronize(self.dev)
                 wp = (w, buf, mode)
                 self._wpacked[name] = wp
             ts = None

@@ -79,7 +79,10 @@ int aoc_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, const
  * padding) and the per-(sample, channel) affine that precedes the convolution in the reference is fused into the
  * operand path:
  *     x_eff = relu?(x * in_a[n,c] + in_b[n,c])      (GroupNorm apply + ReLU, GCT gate, IA gate; each optional)
- * w_packed comes from aoc_conv_pack_weights with the SAME operand_mode (size aoc_conv_packed_weight_bytes).  Requires
+ * w_packed comes from aoc_conv_pack_weights with the SAME operand_mode (size aoc_conv_packed_weight_bytes) and must be
+ * COMPLETE when the convolution is launched (synchronise the stream once after packing): under programmatic dependent
+ * launch (option conv_pdl, default on) the kernel's weight-copy warp starts before the preceding kernel of the stream
+ * has finished -- weights are constants of the model.  Requires
  * ldx % 4 == 0, stride in {1, 2}; Cin <= 1024 when an input affine is given.  chunk_stages <= 0 selects the default (8). */
 #define AOC_CONV_TF32X3 0
 #define AOC_CONV_SPLIT_F16 1
