@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+int g_glue_pdl = 0;      // measured slower: the coefficient kernels stay normal launches
 }  // namespace aoc
 
 namespace aoc { extern int g_conv_chunk; extern int g_conv_dbg; extern int g_conv_splitk; extern int g_conv_narrow_nit; extern int g_conv_pdl; extern int g_match_f16; extern int g_conv_halo; extern int g_match_fast; extern int g_match_collector; extern int g_conv_tail; extern int g_conv_tail_min_stages; }
@@ -30,6 +31,7 @@ extern "C" int aoc_set_option(const char* key, int value) {
     if (key && !strcmp(key, "conv_tail")) { aoc::g_conv_tail = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_halo")) { aoc::g_conv_halo = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_pdl")) { aoc::g_conv_pdl = value != 0; return AOC_OK; }
+    if (key && !strcmp(key, "glue_pdl")) { aoc::g_glue_pdl = value != 0; return AOC_OK; }
     if (key && !strcmp(key, "conv_narrow_nit") && value >= 0) { aoc::g_conv_narrow_nit = value; return AOC_OK; }
     aoc::set_error("aoc_set_option: unknown option '%s'", key ? key : "(null)");
     return AOC_EINVAL;

@@ -23,6 +23,38 @@ inline int launch_status(const char* what) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// First statement of the small kernels that run between two convolutions (coefficient / statistics / resize glue):
+// "my dependents may be scheduled".  The kernel itself is launched normally (it starts after its predecessor has completed);
+// the NEXT kernel of the stream -- a convolution launched with the programmatic-stream-serialization attribute -- then
+// becomes resident while this one runs and does everything that does not depend on it (barrier init, TMEM allocation,
+// tensor-map prefetch, the first ring of weight stages) before its griddepcontrol.wait.  The dependent grid is only
+// launched once EVERY block of this grid has executed the trigger (or exited), so it can never hold resources a block of
+// this grid still needs.  Without such a dependent the instruction does nothing.
+#ifndef AOC_NO_GLUE_TRIGGER      // (tooling build for the A/B measurement: AOCB200_NVCC_FLAGS=-DAOC_NO_GLUE_TRIGGER)
+#define AOC_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;")
+#else
+#define AOC_PDL_TRIGGER() do { } while (0)
+#endif
+// ... and for a glue kernel that is ITSELF launched as a programmatic dependent (launch_pdl below) of the convolution in
+// front of it: everything after this line sees the previous grid's writes.  A no-op under a normal launch.
+#define AOC_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute: the grid may be scheduled as soon as
+// every block of the previous kernel of the stream has triggered (the convolution does so at its start) or exited, i.e. its
+// blocks start on an SM the moment the previous kernel's CTA there retires instead of after a full launch round trip behind
+// the completed grid.  The kernel MUST execute AOC_PDL_WAIT() before it touches global memory.
+extern int g_glue_pdl;                       // aoc_set_option("glue_pdl", 0 / 1)
+template <typename... P, typename... A>
+inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = g_glue_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // Function attributes (opt-in dynamic shared memory) and the SM count belong to a DEVICE, not to the process: a host
 // that drives engines on several GPUs from one process must set / query them once per device ordinal.
 constexpr int AOC_MAX_DEVICES = 64;

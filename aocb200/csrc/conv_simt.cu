@@ -240,6 +240,7 @@ __global__ void dwconv3x3_kernel(const float* __restrict__ x, const float* __res
 // 3x3 stride-2 pad-1 max pool (resnet.py:113), NHWC, C % 4 == 0.
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y,
                                     int N, int H, int W, int C, int Ho, int Wo) {
+    AOC_PDL_TRIGGER();
     int C4 = C >> 2;
     long long total = (long long)N * Ho * Wo * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(KTH_THREADS) kth_largest_kernel(const float* _
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                       const float* __restrict__ b, float* __restrict__ y, int N,
                                                       int M, int K, int ldx, int ldy, int act) {
+    AOC_PDL_TRIGGER();
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= N * M) return;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 
 // out[n, c] = sum_n' v[n', c] - v[n, c]   (conditioning_block x_delta / decoder _delta_head), written at ld/offset
 __global__ void delta_sum_kernel(const float* __restrict__ v, float* __restrict__ out, int N, int C, int ldo) {
+    AOC_PDL_TRIGGER();
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s = 0.f;

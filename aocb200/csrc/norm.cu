@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256, 4) affine_stats_partial(const float* __re
 // serial chain over the slabs (101 for a 121 x 213 map) that made this tiny kernel 5-12 us long is 13 steps instead of 26 x 4.
 __global__ void __launch_bounds__(256) channel_stats_final(const double* __restrict__ part, int S, int C2,
                                                            double* __restrict__ stats) {
+    AOC_PDL_TRIGGER();
     __shared__ double sm[8][33];
     const int n = blockIdx.y;
     const int c = blockIdx.x * 32 + threadIdx.x, l = threadIdx.y;
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(256) channel_stats_final(const double* __restr
 __global__ void gn_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int C, int groups, int HW, float eps,
                                  float* __restrict__ a, float* __restrict__ b) {
+    AOC_PDL_TRIGGER();
     int n = blockIdx.x;
     int cpg = C / groups;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -191,6 +193,7 @@ __global__ void gn_coeffs_kernel(const double* __restrict__ stats, const float* 
 __global__ void gct_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ alpha,
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   const float* __restrict__ pre, int C, float eps, float* __restrict__ a) {
+    AOC_PDL_TRIGGER();
     __shared__ double red[32];
     __shared__ double s_mean;
     int n = blockIdx.x;
@@ -222,6 +225,7 @@ __global__ void gct_coeffs_kernel(const double* __restrict__ stats, const float*
 }
 
 __global__ void gap_from_stats_kernel(const double* __restrict__ stats, int C, float inv_hw, float* __restrict__ out) {
+    AOC_PDL_TRIGGER();
     int n = blockIdx.y;
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) out[(size_t)n * C + c] = (float)(stats[(size_t)n * 2 * C + c] * (double)inv_hw);
@@ -232,6 +236,7 @@ __global__ void affine_nc_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ res, const float* __restrict__ res_scale,
                                  float* __restrict__ y, int HW, int C, int ldx, int ldy, int ldres, int relu,
                                  long long total4) {
+    AOC_PDL_TRIGGER();
     int C4 = C >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -292,6 +297,8 @@ __global__ void __launch_bounds__(256) gn_coeffs_tiles_kernel(const float* __res
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int C, int groups, int HW,
                                                               float eps, float* __restrict__ a, float* __restrict__ b) {
+    AOC_PDL_TRIGGER();
+    AOC_PDL_WAIT();                                   // launched as a programmatic dependent of the convolution (launch_pdl)
     __shared__ double sm[256];
     __shared__ double tot[64];
     __shared__ float s_rstd, s_mean;
@@ -434,8 +441,8 @@ extern "C" int aoc_gn_coeffs_tiles_f32(const float* tile_stats, int tiles_per_im
                                        cudaStream_t stream) {
     AOC_CHECK_ARG(tile_stats && gamma && beta && a && b && tiles_per_image > 0, "bad args");
     AOC_CHECK_ARG(groups > 0 && C % groups == 0 && 2 * (C / groups) <= 64, "C / groups must be <= 32");
-    gn_coeffs_tiles_kernel<<<dim3(groups, N), 256, 0, stream>>>(tile_stats, tiles_per_image, gamma, beta, C, groups, HW,
-                                                               eps, a, b);
+    launch_pdl(gn_coeffs_tiles_kernel, dim3(groups, N), dim3(256), 0, stream, tile_stats, tiles_per_image, gamma, beta, C,
+               groups, HW, eps, a, b);
     return launch_status("aoc_gn_coeffs_tiles_f32");
 }
 

@@ -20,6 +20,7 @@ __global__ void nchw3_to_nhwc4_kernel(const float* __restrict__ x, float* __rest
 // convolution over this tensor (tap a' of the 4 covers source taps r = 2 a' + py - 1): the stem runs 16 stages of 16 real
 // channels instead of 49 stages of 4 real + 12 zero channels.
 __global__ void image_to_s2d16_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int H2p, int W2p) {
+    AOC_PDL_TRIGGER();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // (output pixel, quarter = source pixel of the block)
     if (idx >= H2p * W2p * 4) return;
     const int q = idx & 3, pix = idx >> 2;
@@ -77,6 +78,7 @@ __device__ __forceinline__ void lin_coords(int dst, float scale, int in, int& i0
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, const uint8_t* __restrict__ ids,
                                        const float* __restrict__ table, int n_table, float* __restrict__ y, int N,
                                        int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy, float sh, float sw) {
+    AOC_PDL_TRIGGER();
     int C4 = C >> 2;
     long long total = (long long)N * Ho * Wo * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -169,6 +171,7 @@ __global__ void resize_bicubic_kernel(const float* __restrict__ x, float* __rest
 // order, minus the terms whose weight is exactly zero -- is that of resize_bicubic_kernel, so the results are bit-identical.
 __global__ void __launch_bounds__(256) resize_bicubic2x_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi,
                                                                int Wi, int Ho, int Wo, int C, int ldx, int ldy, float sh, float sw) {
+    AOC_PDL_TRIGGER();
     const int C4 = C >> 2;
     const int Hb = (Ho + 1) >> 1, Wb = (Wo + 1) >> 1;                  // 2 x 2 output blocks
     const long long total = (long long)N * Hb * Wb * C4;
@@ -310,6 +313,7 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint32_t v, long long 
 // out = a (op) b over n floats; op 0: a + b, 1: a * b   (per-(sample, channel) coefficient vectors: a few thousand values)
 __global__ void vec_op_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n,
                               int op) {
+    AOC_PDL_TRIGGER();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = op == 0 ? a[i] + b[i] : a[i] * b[i];
 }
@@ -424,6 +428,7 @@ extern "C" int aoc_vec_op_f32(const float* a, const float* b, float* out, int n,
 namespace aoc {
 __global__ void copy_channels_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int C, int ldx,
                                      int ldy) {
+    AOC_PDL_TRIGGER();
     int C4 = C >> 2;
     long long total = rows * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;

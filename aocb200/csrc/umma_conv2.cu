@@ -67,6 +67,26 @@ constexpr int C2_REGS_MISC = C2_NS == 2 ? 40 : 32;
 static_assert(C2_XW * C2_REGS_XFORM + 8 * C2_REGS_DRAIN + 4 * C2_REGS_MISC <= (C2_XW + 12) * C2_LAUNCH_REGS,
               "setmaxnreg.inc can only take what the CTA's own warps released: an over-subscribed budget blocks forever");
 
+// Division of a non-negative int (< 2^31) by a launch constant as multiply-high + shift (the host computes the pair):
+// the tile decode below is ten divisions by kernel parameters, inlined into the loop of every warp role -- as hardware-less
+// integer divisions they were 1 157 of the 4 096 instructions of the split-K kernel, a quarter of a code image that is
+// already twice the 32 KB instruction cache and is fetched cold at the start of every launch.
+struct FastDiv { uint32_t mul, shr; };
+inline FastDiv fastdiv_make(int d) {
+    FastDiv f = {0u, 0u};
+    if (d > 1) {
+        uint32_t l = 0;
+        while ((1u << l) < (uint32_t)d) ++l;                 // ceil(log2 d)
+        const uint64_t pw = 1ull << (31 + l);
+        f.mul = (uint32_t)((pw + (uint64_t)d - 1) / (uint64_t)d);
+        f.shr = l - 1;
+    }
+    return f;
+}
+__device__ __forceinline__ int fastdiv(int x, FastDiv f) {       // f.mul == 0: divisor 1
+    return f.mul ? (int)(__umulhi((uint32_t)x, f.mul) >> f.shr) : x;
+}
+
 struct Conv2P {
     const uint8_t* w; const float* bias; const float* res; const float* in_a; const float* in_b; float* y;
     float* tile_stats;      // optional [pixel tiles][2][Cout]: per-tile sum / sum of squares of the stored output
@@ -82,7 +102,15 @@ struct Conv2P {
     int vec_out;
     int* overflow;          // optional device word: set to 1 when a split-fp16 activation operand reaches the fp16 range (|x| >= 6e4)
     int dbg;                // tooling build only (tools/conv_attrib.py): ablation bits, see C2_DBG
+    FastDiv fd_ksplit, fd_nrc, fd_tiles_n, fd_tpi, fd_tiles_x;    // set by c2_set_fastdiv() once the launcher has fixed the schedule
 };
+static void c2_set_fastdiv(Conv2P& q) {
+    q.fd_ksplit = fastdiv_make(q.ksplit);
+    q.fd_nrc = fastdiv_make((q.ncc + 1) >> 1);
+    q.fd_tiles_n = fastdiv_make(q.tiles_n);
+    q.fd_tpi = fastdiv_make(q.tiles_x * q.tiles_y);
+    q.fd_tiles_x = fastdiv_make(q.tiles_x);
+}
 
 #ifdef AOC_CONV_TRACE   // tooling build only (tools/conv_trace.py): keeps the production kernel's code small
 // stage index of an event = running stage count of CTA 0 (tile ordinal x stages per tile + stage): short-K layers show several tiles
@@ -93,9 +121,13 @@ struct Conv2P {
 // 1 no weight copies (the barrier is completed by a plain arrive), 2 no activation TMA, 4 no correction MMAs,
 // 8 no transform arithmetic (zeros are stored), 16 no main MMAs
 #define C2_DBG(bit) ((p.dbg & (bit)) != 0)
+// whole-kernel milestones of CTA 0 (event row 15): 0 kernel entry, 1 prologue done, 2 previous grid complete (transform warp 0),
+// 3 first activation TMA issued, 4 accumulators drained, 5 partial tile written + arrived, 6 all K slices arrived, 7 finished
+#define C2_MARK(k) do { if (p.trace && blockIdx.x == 0) p.trace[15 * 256 + (k)] = clock64(); } while (0)
 #else
 #define C2_TRACE(ev, st) do { } while (0)
 #define C2_DBG(bit) false
+#define C2_MARK(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -185,7 +217,12 @@ struct C2Cfg {
 // (tile, K slice): the slice covers the raw stages [r0, r1) of the (tap, 32-channel box) sequence, i.e. the operand
 // stages [it0, it1).  Without it the K fields are the whole range and fold away (the issue loops of the plain kernel must
 // not carry them: a Tile kept in local memory cost 18 % on the large layers).
-struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0, tile, nsl; };   // tile: flat tile index; nsl: K slices of it
+struct Tile { int n, ho0, wo0, n0, ks, r0, r1, it0, it1, tap0, cc0, tile, nsl; };
+#ifndef AOC_CONV_NO_HOIST     // (tooling build for the A/B measurement of the hoisted first-tile decode)
+#define C2_FIRST_TILE(t) ((t) == (int)blockIdx.x)
+#else
+#define C2_FIRST_TILE(t) false
+#endif   // tile: flat tile index; nsl: K slices of it
 
 // SK: 0 = every work item is a whole tile, 1 = split-K of every tile (small maps), 2 = tail splitting (K slices for the tiles
 // of the partial last wave only)
@@ -244,30 +281,30 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                 // tail splitting: the whole waves of tiles run unsplit, the tiles of the last, partial wave are cut into
                 // `ksplit` K slices each so that the wave fills the chip (items n_plain .. : tile-major, slice fastest)
                 if (w < p.n_plain) { t = w; tl.ks = 0; nsl = 1; }
-                else { const int u = w - p.n_plain; t = p.n_plain + u / p.ksplit; tl.ks = u - (t - p.n_plain) * p.ksplit; }
+                else { const int u = w - p.n_plain, uq = fastdiv(u, p.fd_ksplit); t = p.n_plain + uq; tl.ks = u - uq * p.ksplit; }
             } else {
-                t = w / p.ksplit;
+                t = fastdiv(w, p.fd_ksplit);
                 tl.ks = w - t * p.ksplit;
             }
             tl.nsl = nsl;
             const int R = p.taps * nrc;
-            tl.r0 = R * tl.ks / nsl;
-            tl.r1 = R * (tl.ks + 1) / nsl;
-            int tp = tl.r0 / nrc;
+            tl.r0 = nsl == 1 ? 0 : fastdiv(R * tl.ks, p.fd_ksplit);
+            tl.r1 = nsl == 1 ? R : fastdiv(R * (tl.ks + 1), p.fd_ksplit);
+            int tp = fastdiv(tl.r0, p.fd_nrc);
             tl.tap0 = tp;
             tl.cc0 = 2 * (tl.r0 - tp * nrc);
             tl.it0 = tp * p.ncc + tl.cc0;
-            tp = tl.r1 / nrc;
+            tp = fastdiv(tl.r1, p.fd_nrc);
             tl.it1 = tp * p.ncc + min(2 * (tl.r1 - tp * nrc), p.ncc);
         } else {
             tl.ks = 0; tl.r0 = 0; tl.r1 = p.taps * nrc; tl.tap0 = 0; tl.cc0 = 0; tl.it0 = 0; tl.it1 = nIt; tl.nsl = 1;
         }
         tl.tile = t;
-        const int mt = t / p.tiles_n;
+        const int mt = fastdiv(t, p.fd_tiles_n);
         tl.n0 = (t - mt * p.tiles_n) * TN;
-        tl.n = mt / tpi;
+        tl.n = fastdiv(mt, p.fd_tpi);
         const int trem = mt - tl.n * tpi;
-        const int tyi = trem / p.tiles_x, txi = trem - tyi * p.tiles_x;
+        const int tyi = fastdiv(trem, p.fd_tiles_x), txi = trem - tyi * p.tiles_x;
         tl.ho0 = tyi * p.th;
         tl.wo0 = txi << p.tw_log2;
         return tl;
@@ -276,7 +313,17 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
     // Programmatic dependent launch: the next kernel of the stream may be scheduled onto SMs as this grid's CTAs retire
     // and run its prologue (barrier init, TMEM allocation, descriptor fetch) under our tail; every role that touches
     // global memory first executes griddepcontrol.wait (= the previous grid has completed and its writes are visible).
+    if (threadIdx.x == 0) C2_MARK(0);
     asm volatile("griddepcontrol.launch_dependents;");
+    // The first work item of this CTA is decoded HERE, before the wait for the previous grid: ten integer divisions on
+    // kernel parameters that miss the constant cache on first touch were ~1 500-3 000 cycles between "previous grid complete"
+    // and the first activation TMA (tools/conv_marks.py), paid again by every role at the top of its loop -- and a layer of
+    // the 31 x 54 backbone maps has exactly one work item per CTA.  (The empty asm pins the values: without it the
+    // compiler re-materialises the decode inside each role, after the wait.)
+    Tile tile0 = decode((int)blockIdx.x);
+    asm volatile("" : "+r"(tile0.n), "+r"(tile0.ho0), "+r"(tile0.wo0), "+r"(tile0.n0), "+r"(tile0.ks), "+r"(tile0.r0),
+                 "+r"(tile0.r1), "+r"(tile0.it0), "+r"(tile0.it1), "+r"(tile0.tap0), "+r"(tile0.cc0), "+r"(tile0.tile),
+                 "+r"(tile0.nsl));
     if (warp == C2_XW + 9 && lane == 0) {
         if (HALO) {
             // RAW_FULL(0..2) / RAW_EMPTY(0..2): raw halo ring (released by the eight transform warps); RAW_FULL(3 + b) /
@@ -297,14 +344,24 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
         tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
         tmem_relinquish();
     }
+    // the activation tensor map is a kernel parameter: its descriptor fetch (the first cp.async.bulk.tensor would pay it
+    // after the wait below) is started here, under the previous grid's tail
+    if (warp == C2_XW + 8 && lane == 0)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) C2_MARK(1);
     // transform, drain and the activation TMA producer wait for the previous grid; the weight producer (warp C2_XW + 9) does
     // NOT: the packed weight image is a constant of the model (complete before the first launch that uses it -- contract of
     // aoc_conv2d_nhwc_tc), so its first ring of stages is fetched from HBM while the previous layer's last CTAs finish
-    if (warp < C2_XW + 9) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // The activation producer (warp C2_XW + 8) waits LATER, immediately in front of its first tensor copy: its way there --
+    // role dispatch, register hand-back, tile coordinates, barrier set-up -- is ~60 instructions of code that is cold in the
+    // instruction cache at every launch (the kernel image is twice the 32 KB L1.5), measured at ~2 400 cycles between
+    // "previous grid complete" and the first copy (tools/conv_marks.py); walked before the wait it overlaps the previous grid.
+    if (warp < C2_XW + 8) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) C2_MARK(2);
 
     if (warp < C2_XW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
@@ -321,7 +378,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             int tab_n = -1;
             float amax = 0.f;
             for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-                const Tile tl = decode(t);
+                const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
                 if (affine && tl.n != tab_n) {
                     asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
                     const int cpad = p.ncc * C2_KC;
@@ -418,7 +475,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
         int pend = -1;                                                       // operand slot stored but not yet published
         float amax = 0.f;                                                    // largest |operand| this thread converted to fp16
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-            const Tile tl = decode(t);
+            const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
             if (affine && tl.n != tab_n) {
                 // per-(sample, channel) coefficient table of this image; only the transform warps touch it
@@ -582,7 +639,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
         int b = 0, cb = 0;
         uint32_t ph0 = 0u, ph1 = 0u, pcf0 = 0u, pcf1 = 0u;
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-            const Tile tl = decode(t);
+            const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
             float acc[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[c] = 0.f;
@@ -624,6 +681,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             __syncwarp();
             if (lane == 0) mbar_arrive(CORR_EMPTY(cb));          // the issuer may start the next tile on this buffer
             if (threadIdx.x == C2_XT) C2_TRACE(13, tl.it0);
+            if (threadIdx.x == C2_XT && t == (int)blockIdx.x) C2_MARK(4);
             if (SK == 2 && tl.nsl > 1) {
                 // ---- tail splitting: slices 1.. park their partial accumulators (this thread's row, its NC channels) in the
                 // workspace and move on; slice 0 waits for them, adds them in slice order (deterministic) and runs the normal
@@ -803,11 +861,13 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (threadIdx.x == C2_XT) {
                     atomicAdd(cnt, 1);
+                    C2_MARK(5);
                     int v;
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
                     } while (v < p.ksplit);
                     __threadfence();
+                    C2_MARK(6);
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 {
@@ -846,6 +906,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                     }
                 }
                 asm volatile("bar.sync 2, 256;" ::: "memory");          // every thread of this slice has read the partial sums
+                if (threadIdx.x == C2_XT) C2_MARK(7);
                 if (threadIdx.x == C2_XT && atomicAdd(cnt, 1) == 2 * p.ksplit - 1) *cnt = 0;
             }
         }
@@ -855,22 +916,24 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             // ===== activation TMA producer: one 128-pixel x 32-channel box per two operand stages =====
             int sr = 0;
             uint32_t pr = 0;
+            bool waited = false;                 // griddepcontrol.wait executed (see the prologue)
             if constexpr (HALO) {
                 // halo: ONE box per 32-channel group -- the (16 + 2d) x (8 + 2d) pixel patch all nine taps read
                 const uint32_t bytes = (uint32_t)((C2H_TW + 2 * p.dil) * (C2H_TH + 2 * p.dil) * 128);
                 for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-                    const Tile tl = decode(t);
+                    const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
                     for (int cb = 0; cb < nrc; ++cb) {
                         mbar_wait(RAW_EMPTY(sr), pr ^ 1u);
                         C2_TRACE(0, 18 * cb);
                         mbar_arrive_expect_tx(RAW_FULL(sr), bytes);
+                        if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
                         tma_load_4d(raw0 + sr * C2H_RAW_BYTES, &tmapA, cb * C2_RKC, tl.wo0 - p.dil, tl.ho0 - p.dil, tl.n, RAW_FULL(sr));
                         if (++sr == C2H_NRAW) { sr = 0; pr ^= 1u; }
                     }
                 }
             } else
             for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-                const Tile tl = decode(t);
+                const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
                 const int wbase = tl.wo0 * p.stride - p.pad, hbase = tl.ho0 * p.stride - p.pad;
                 int tap = tl.tap0, rc = tl.cc0 >> 1;
                 int r = tap / p.kw, s = tap - r * p.kw;
@@ -881,6 +944,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                         mbar_arrive(RAW_FULL(sr));
                     } else {
                         mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
+                        if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
                         tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil, hbase + r * p.dil,
                                     tl.n, RAW_FULL(sr));
                     }
@@ -899,7 +963,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             int sb_ = 0;
             uint32_t pb = 0;
             for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-                const Tile tl = decode(t);
+                const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
                 const int rb = tl.n0 / C2_WRB;
                 const uint8_t* wsrc = p.w + (size_t)rb * nIt * C2_WCHUNK;
                 const uint32_t sub = (uint32_t)(tl.n0 % C2_WRB) * 32u;       // byte offset of row n0 inside a 4096 B block
@@ -992,7 +1056,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             }
         } else
         for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
-            const Tile tl = decode(t);
+            const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
             int in_chunk = 0;
             // Two stages (one operand pair) per iteration where the pair lies inside the tile: one barrier wait, one
             // tcgen05 fence, one elect and one warp sync for both -- this warp's iteration is the period of the kernel
@@ -1105,7 +1169,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             // the CORR buffer of this tile must have been read out by the drain warps (two tiles ago when double buffered)
             if (cb == 0) { mbar_wait(CORR_EMPTY(0), pc0 ^ 1u); pc0 ^= 1u; }
             else         { mbar_wait(CORR_EMPTY(1), pc1 ^ 1u); pc1 ^= 1u; }
-            const Tile tl = decode(t);
+            const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
             for (int it = tl.it0; it < tl.it1;) {                      // two stages per iteration, as in the MAIN issuer
                 const int n = ((so & 1) == 0 && it + 1 < tl.it1) ? 2 : 1;
                 if ((so & 1) == 0) mbar_wait(OP_FULL(so >> 1), po);
@@ -1296,6 +1360,7 @@ static int launch_conv2(const CUtensorMap& map, const Conv2P& p, int tiles, void
             q.ws = (float*)((char*)workspace + C2_WS_HEADER); q.ws_cnt = (int*)workspace;
         }
     }
+    c2_set_fastdiv(q);
     const int items = q.tail_mode ? q.n_plain + (q.total_tiles - q.n_plain) * q.ksplit : q.total_tiles * q.ksplit;
     const int grid = items < sms ? items : sms;                       // persistent: one CTA per SM walks the work list
     cudaLaunchAttribute attr_pdl[1];
@@ -1326,6 +1391,7 @@ static int launch_conv2_halo(const CUtensorMap& map, const Conv2P& p, int tiles,
     q.tiles_n = cdiv(p.Cout, TN);
     q.total_tiles = tiles * q.tiles_n;
     q.ksplit = 1; q.ws = nullptr; q.ws_cnt = nullptr;
+    c2_set_fastdiv(q);
     const int sms = device_sms();
     const int grid = q.total_tiles < sms ? q.total_tiles : sms;
     cudaLaunchAttribute attr_pdl[1];
