@@ -57,7 +57,9 @@ int aoc_check_device(int dev);
  * for the tiles of a partial last wave of long K loops.  "match_fast" (default 0): FAST precision mode of the global matching
  * -- one fp16 MMA per product instead of three; the only switch that changes results beyond fp32 rounding (schedules differ in
  * summation order only), off unless a caller asks for it.  "match_collector" (default 0): tcgen05 collector hints on the
- * query operand of the matching contraction (identical results; measured slower, kept as an experiment switch). */
+ * query operand of the matching contraction (identical results; measured slower, kept as an experiment switch).
+ * "glue_pdl" (default 0): programmatic dependent launch of the GroupNorm coefficient kernel itself (identical results;
+ * measured slower). */
 int aoc_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------- convolutions (conv_simt.cu, umma_conv2.cu) */
