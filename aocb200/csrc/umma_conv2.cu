@@ -356,15 +356,19 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
     // transform, drain and the activation TMA producer wait for the previous grid; the weight producer (warp C2_XW + 9) does
     // NOT: the packed weight image is a constant of the model (complete before the first launch that uses it -- contract of
     // aoc_conv2d_nhwc_tc), so its first ring of stages is fetched from HBM while the previous layer's last CTAs finish
-    // The activation producer (warp C2_XW + 8) waits LATER, immediately in front of its first tensor copy: its way there --
-    // role dispatch, register hand-back, tile coordinates, barrier set-up -- is ~60 instructions of code that is cold in the
-    // instruction cache at every launch (the kernel image is twice the 32 KB L1.5), measured at ~2 400 cycles between
-    // "previous grid complete" and the first copy (tools/conv_marks.py); walked before the wait it overlaps the previous grid.
-    if (warp < C2_XW + 8) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) C2_MARK(2);
+    // Nobody waits for the previous grid HERE.  Each role executes griddepcontrol.wait immediately in front of its first
+    // access to global memory, so that its way there -- role dispatch, register re-partitioning, loop set-up: code that is
+    // cold in the instruction cache at every launch (the kernel image is twice the 32 KB L1.5; measured at ~2 400 cycles
+    // between "previous grid complete" and the first activation copy, tools/conv_marks.py) -- overlaps the previous grid:
+    //   activation producer   in front of its first cp.async.bulk.tensor
+    //   transform warps       in front of the coefficient table loads (in_a / in_b); without an input affine they touch shared
+    //                         and tensor memory only and do not wait at all (the sticky overflow word is write-only)
+    //   drain warps           after their register increase (residual / split-K partial reads, every global write)
+    //   weight producer       never (constants), MMA issuers never (no global memory)
 
     if (warp < C2_XW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REGS_XFORM));
+        bool waited = false;                     // griddepcontrol.wait executed by this thread
         if constexpr (HALO) {
             // ===== halo transform: all eight warps convert the raw halo patch of a channel box (P pixels x 32 channels) ONCE
             // into the split-fp16 operand tiles [k-group of 8 channels][pixel][16 B] (hi and lo); item = (pixel, k-group) =====
@@ -380,6 +384,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
                 const Tile tl = C2_FIRST_TILE(t) ? tile0 : decode(t);
                 if (affine && tl.n != tab_n) {
+                    if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
                     asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
                     const int cpad = p.ncc * C2_KC;
                     for (int c = threadIdx.x; c < cpad; c += C2_XT) {
@@ -479,6 +484,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
             const int hb = (tl.ho0 + ty) * p.stride - p.pad, wb = (tl.wo0 + tx) * p.stride - p.pad;
             if (affine && tl.n != tab_n) {
                 // per-(sample, channel) coefficient table of this image; only the transform warps touch it
+                if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
                 asm volatile("bar.sync 1, %0;" ::"n"(C2_XT) : "memory");
                 const int cpad = p.ncc * C2_KC;
                 for (int c = threadIdx.x; c < cpad; c += C2_XT) {
@@ -631,6 +637,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
         // (the register file is re-partitioned between the warpgroups: these two hold TN/2 accumulators + a 32-wide
         // tcgen05.ld per thread; the producer / issuer warpgroup gives its share back)
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REGS_DRAIN));
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         constexpr int NC = TN / 2;
         const int dwp = warp - C2_XW;
         const int q = dwp & 3, half = dwp >> 2;
@@ -944,7 +951,7 @@ __global__ void __launch_bounds__(C2Cfg<TN, F16, HALO>::THREADS, 1) conv2_kernel
                         mbar_arrive(RAW_FULL(sr));
                     } else {
                         mbar_arrive_expect_tx(RAW_FULL(sr), C2_RAW_BYTES);
-                        if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; }
+                        if (!waited) { asm volatile("griddepcontrol.wait;" ::: "memory"); waited = true; C2_MARK(2); }
                         tma_load_4d(raw0 + sr * C2_RAW_BYTES, &tmapA, rc * C2_RKC, wbase + s * p.dil, hbase + r * p.dil,
                                     tl.n, RAW_FULL(sr));
                     }
