@@ -12,6 +12,7 @@ timeout 200 python tools/conv_table.py > $O/${P}_conv_table.txt 2>&1
 timeout 100 python tools/frame_breakdown.py > $O/${P}_frame_breakdown.txt 2>&1
 timeout 100 python tools/step_times.py > $O/${P}_step_times.txt 2>&1
 AOCB200_LIB_TAG=trace timeout 100 python tools/conv_trace.py dec.conv1 dec.l1.conv3 > $O/${P}_conv_trace.txt 2>&1
+AOCB200_LIB_TAG=trace timeout 100 python tools/conv_marks.py > $O/${P}_conv_marks.txt 2>&1
 AOCB200_LIB_TAG=trace timeout 200 python tools/conv_attrib.py > $O/${P}_conv_attrib.txt 2>&1
 timeout 900 tools/ncu_captures.sh $P
 ls $O | wc -l
