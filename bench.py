@@ -540,7 +540,7 @@ def main():
                 ("conv", "conv2_kernel (tcgen05 implicit-GEMM convolution, split-fp16 operands; per-tap and halo variants)", 3.0,
                  "achieved counts algorithmic fp32 FLOPs once; the kernel issues 3 kind::f16 MMAs per product (hi*hi, lo*hi, "
                  "hi*lo), so its hardware ceiling is peak/3; traffic = DRAM bytes of the largest layer's launch (decoder conv1, halo "
-                 "variant, algorithmic 277 MB) from profiles/r2_conv2_dec_conv1_ncu_full.txt", 251941376),
+                 "variant, algorithmic 277 MB) from profiles/r2z_conv2_dec_conv1_ncu_full.txt", 253296896),
                 ("match", "match_tc_kernel (tcgen05 global matching with fused segmented-min epilogue, split-fp16 operands)", 3.0,
                  "achieved counts algorithmic fp32 FLOPs once (2 x queries x padded bank rows x 100); the kernel issues 3 "
                  "kind::f16 MMAs per product, so its hardware ceiling is peak/3", None)):
