@@ -272,6 +272,7 @@ def kernel_profile(model, frames, first, device, n_frames):
     L.profile_graph = {}
     prof = {n: [] for n in names}        # (milliseconds, args) per launch, frame-major
     st = Stepper(model, frames, first, K_OBJ, device, False)
+    n_frames = max(1, min(n_frames, frames.shape[0] - 3))       # the clip holds 1 + warm-up + steps frames (warm-up >= 3)
     for _ in range(2):                   # captures every segment variant (with / without decoder memory)
         st.step()
     km_rows = []
