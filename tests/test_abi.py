@@ -37,6 +37,11 @@ def test_version_and_error_string(built_lib):
 def test_workspace_queries(built_lib):
     # whole-wave slabs (norm.cu::stats_slab): 6 samples x 148 slabs = one wave of 148 SMs x 6 resident blocks
     assert built_lib.channel_stats_workspace_bytes(6, 25773, 256) == 6 * 148 * 2 * 256 * 8
+    # ... for every statistics launch of the 480p frame: the slabs of the six samples fill one wave of resident blocks
+    # (148 SMs x 6 for the statistics kernel, x 4 for the apply + statistics kernel) and never spill into a second one
+    for hw, c in ((25773, 64), (25773, 128), (25773, 256), (6527, 128), (6527, 256), (6527, 512), (6527, 640)):
+        slabs = built_lib.channel_stats_workspace_bytes(6, hw, c) // (6 * 2 * c * 8)
+        assert 6 * slabs <= 148 * 6 and 6 * slabs >= 0.9 * 148 * 4, (hw, c, slabs)
     assert built_lib.bank_workspace_bytes(25773, 6) > 0
     assert built_lib.kmeans_workspace_bytes(25773, 6, 16) > 0
     assert built_lib.head_pool_workspace_bytes(25773) > 0
